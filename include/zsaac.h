@@ -1,0 +1,140 @@
+/*
+ * zsaac.h — C ABI of the B200-native related-caption retrieval library (libzsaac_b200.so).
+ *
+ * The reference (XinMing0411/zero-shot-AAC) has no FFI of its own: its hot path is four
+ * module-level Python functions that call torch.  Each entry point below replaces the torch
+ * calls made at one reference call site; the Python host (zero-shot-aac_b200/) keeps the
+ * reference's function names and signatures and binds these symbols through ctypes
+ * (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 (ZS_OK) or a negative zs_status; the message of the last
+ *     failure on the calling thread is available from zs_last_error()
+ *   - all tensor pointers are DEVICE pointers on the context's device unless the name says host
+ *   - work is enqueued on the cudaStream_t passed as `stream` (NULL = legacy default stream);
+ *     no entry point synchronises the host except where stated (workspace growth)
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU zs_create fails
+ *   - plain C types only; no torch / C++ types cross this boundary
+ */
+#ifndef ZSAAC_H_
+#define ZSAAC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS_ABI_VERSION 1
+
+typedef struct zs_ctx zs_ctx;
+
+typedef enum zs_status {
+  ZS_OK = 0,
+  ZS_ERR_INVALID = -1,     /* bad argument (k out of range, d not supported, null pointer ...) */
+  ZS_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                              */
+  ZS_ERR_NO_DEVICE = -3,   /* no sm_100 device: this library has no fallback path              */
+  ZS_ERR_STATE = -4,       /* call order violated (search before the bank was uploaded ...)    */
+  ZS_ERR_KERNEL = -5       /* a kernel reported a pipeline time-out through the device flag    */
+} zs_status;
+
+typedef enum zs_dtype {
+  ZS_F32 = 0,
+  ZS_BF16 = 1
+} zs_dtype;
+
+/* Limits of the fused kernel. */
+#define ZS_MAX_K 32        /* top-k list length held in registers per query row              */
+#define ZS_DIM_MULTIPLE 64 /* embedding dim must be a multiple of the 128-byte bf16 K block  */
+#define ZS_MAX_DIM 4096
+
+/* ---- context ---------------------------------------------------------------------------- */
+
+/* Create a context bound to CUDA device `device`.  Owns the bf16 bank copy and the search
+ * workspaces.  One context per GPU; multi-GPU runs use one process (and one context) per GPU. */
+int zs_create(zs_ctx** out, int device);
+int zs_destroy(zs_ctx* ctx);
+
+/* ---- bank (replaces load_data's `F.normalize(torch.cat(...).to('cuda'), dim=-1)`,
+ *      reference data_handing/embeddings_related_generator.py:15-17, _wavcaps.py:16-18) ---- */
+
+/* Allocate (or re-allocate) library-owned storage for `n_rows` bank rows of dimension `d`
+ * in bf16.  Synchronises the device if storage has to be (re)allocated. */
+int zs_bank_alloc(zs_ctx* ctx, int64_t n_rows, int d);
+
+/* Convert `n_rows` rows starting at `rows` (row-major, leading dimension d, dtype `in_dtype`)
+ * to bf16 and store them at bank rows [dst_row, dst_row + n_rows).  With normalize != 0 every
+ * row is scaled by 1 / max(||row||_2, 1e-12) in fp32 before the cast (F.normalize semantics,
+ * eps = 1e-12).  May be called repeatedly to fill the bank block by block. */
+int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_row,
+                   int in_dtype, int normalize, void* stream);
+
+/* out[i, :] = in[i, :] / max(||in[i, :]||_2, 1e-12), fp32 in and out (in-place allowed): the
+ * fp32 unit-row bank load_data returns to its caller (reference
+ * embeddings_related_generator.py:17).  d must be a multiple of 4.  Needs no bank. */
+int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_rows, int d,
+                          void* stream);
+
+/* Number of rows / dimension currently allocated (0 when no bank). */
+int64_t zs_bank_rows(const zs_ctx* ctx);
+int zs_bank_dim(const zs_ctx* ctx);
+
+/* ---- search (replaces process_data's per-item
+ *      `torch.cosine_similarity(F.normalize(q), bank).topk(k)`,
+ *      reference data_handing/embeddings_related_generator.py:21-22, and
+ *      `prefix @ bank.T -> softmax -> topk` of utils.py:133-135) ------------------------- */
+
+/* Pre-size the workspaces for searches of up to Q queries with top-k `k` so that zs_search
+ * does not allocate (and therefore never synchronises). */
+int zs_reserve(zs_ctx* ctx, int64_t Q, int k);
+
+/* Fused similarity + top-k of Q queries against the uploaded bank.
+ *   queries          [Q, d] row-major, dtype q_dtype
+ *   normalize_queries != 0: each query is L2-normalised (eps 1e-12) in fp32 before the bf16 cast
+ *   self_index       nullable [Q] int64: GLOBAL bank index that query i must not return
+ *                    (self-exclusion); entries < 0 mean "no exclusion"
+ *   index_offset     added to every returned index (first global row of this bank shard)
+ *   out_scores       [Q, k] fp32, descending; ties broken by ascending index
+ *   out_indices      [Q, k] int64 global indices
+ * Requires 1 <= k <= min(ZS_MAX_K, bank rows [- 1 with self exclusion]). */
+int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k,
+              int normalize_queries, const int64_t* self_index, int64_t index_offset,
+              float* out_scores, int64_t* out_indices, void* stream);
+
+/* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
+ * bank chunks) under the total order (score desc, index asc).
+ *   scores  list s of query q starts at scores  + s*list_stride + q*k   (elements)
+ *   indices likewise.  Output [Q, k].  Stand-alone: needs no bank. */
+int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t list_stride,
+             int64_t Q, int k, float* out_scores, int64_t* out_indices, void* stream);
+
+/* Gather rows: out[i, :] = src[indices[i], :] for fp32 [*, d] row-major src (replaces
+ * `valid_text_embs[ids]`, reference embeddings_related_generator.py:23). */
+int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,
+                       const int64_t* indices, int64_t n_idx, float* out, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+
+/* Launch geometry chosen for a (Q, k) search on the current bank: number of bank chunks a
+ * query tile is split into, 256-row bank tiles per chunk, CTAs launched.  For tests / bench. */
+int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_chunk, int* n_ctas);
+
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t zs_launch_count(const zs_ctx* ctx);
+
+/* Test hook: run the same TMA + tcgen05 pipeline but write the full fp32 score matrix
+ * [Q, n_bank] (row-major) instead of the top-k.  Small shapes only. */
+int zs_debug_scores(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype,
+                    int normalize_queries, float* out_scores, void* stream);
+
+/* Name of the dominant kernel (for ncu -k) and ABI version. */
+const char* zs_kernel_name(void);
+int zs_abi_version(void);
+
+/* Thread-local message describing the last non-zero status returned on this thread. */
+const char* zs_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSAAC_H_ */

@@ -1,0 +1,181 @@
+// aux_kernels.cuh — the small HBM-bound kernels around the fused similarity/top-k kernel:
+//   normalize_cast_kernel : F.normalize(x, dim=-1) (eps 1e-12) + cast to bf16 (or fp32 out)
+//                           (reference embeddings_related_generator.py:17 for the bank, :21 per query)
+//   merge_lists_kernel    : k-way merge of sorted (score, index) lists, order (score desc, index asc)
+//   gather_rows_kernel    : out[i] = src[idx[i]]      (reference embeddings_related_generator.py:23)
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace zs {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  d is a multiple of 64, so every lane handles whole 8-byte/16-byte vectors.
+// The sum of squares is accumulated in a fixed order (lane-strided, then xor butterfly), so the
+// result does not depend on the launch geometry.
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
+                      int d, int normalize) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const InT* src = in + row * d;
+  OutT* dst = out + row * d;
+  float scale = 1.0f;
+  if (normalize) {
+    float ss = 0.0f;
+    for (int c = lane * 4; c < d; c += 128) {
+      float x0, x1, x2, x3;
+      if constexpr (sizeof(InT) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c);
+        x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+      } else {
+        const uint2 raw = *reinterpret_cast<const uint2*>(src + c);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
+      }
+      ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+    }
+    ss = warp_sum(ss);
+    scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  for (int c = lane * 4; c < d; c += 128) {
+    float x0, x1, x2, x3;
+    if constexpr (sizeof(InT) == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+    } else {
+      const uint2 raw = *reinterpret_cast<const uint2*>(src + c);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
+    }
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(dst + c) = make_float4(x0 * scale, x1 * scale, x2 * scale, x3 * scale);
+    } else {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 * scale, x1 * scale);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 * scale, x3 * scale);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst + c) = packed;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge: one warp per query; lane l owns lists l, l+32, ... (at most MERGE_MAX_LISTS_PER_LANE).
+constexpr int MERGE_MAX_LISTS_PER_LANE = 8;
+constexpr int MERGE_MAX_LISTS = 32 * MERGE_MAX_LISTS_PER_LANE;
+
+struct Cand {
+  float s;
+  long long i;
+  int src;  // lane * MERGE_MAX_LISTS_PER_LANE + slot : makes the order strict even for duplicates
+};
+
+// int32 lists (chunk partials of the fused kernel) mark empty slots with 0x7fffffff
+template <typename IdxT>
+__device__ __forceinline__ long long widen_index(IdxT v) {
+  if (sizeof(IdxT) == 4 && static_cast<long long>(v) == 0x7fffffffll) return 0x7fffffffffffffffll;
+  return static_cast<long long>(v);
+}
+
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
+  if (a.s != b.s) return a.s > b.s;
+  if (a.i != b.i) return a.i < b.i;
+  return a.src < b.src;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
+                   int64_t list_stride, int64_t Q, int k, long long idx_offset,
+                   float* __restrict__ out_scores, long long* __restrict__ out_idx) {
+  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+
+  const long long SENT = 0x7fffffffffffffffll;
+  int head[MERGE_MAX_LISTS_PER_LANE];
+  float hs[MERGE_MAX_LISTS_PER_LANE];
+  long long hi[MERGE_MAX_LISTS_PER_LANE];
+#pragma unroll
+  for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
+    const int list = lane + 32 * l;
+    head[l] = 0;
+    hs[l] = -CUDART_INF_F;
+    hi[l] = SENT;
+    if (list < S) {
+      const int64_t o = static_cast<int64_t>(list) * list_stride + q * k;
+      hs[l] = scores[o];
+      hi[l] = widen_index(idx[o]);
+    } else {
+      head[l] = k;  // exhausted
+    }
+  }
+
+  for (int r = 0; r < k; ++r) {
+    Cand best{-CUDART_INF_F, SENT, 0x7fffffff};
+#pragma unroll
+    for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
+      if (head[l] < k) {
+        const Cand c{hs[l], hi[l], lane * MERGE_MAX_LISTS_PER_LANE + l};
+        if (cand_better(c, best)) best = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Cand other;
+      other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
+      other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+      other.src = __shfl_xor_sync(0xffffffffu, best.src, o);
+      if (cand_better(other, best)) best = other;
+    }
+    if (lane == 0) {
+      out_scores[q * k + r] = best.s;
+      out_idx[q * k + r] = (best.i == SENT) ? -1ll : best.i + idx_offset;
+    }
+    // the owner of the winning list advances it
+#pragma unroll
+    for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
+      if (best.src == lane * MERGE_MAX_LISTS_PER_LANE + l) {
+        ++head[l];
+        if (head[l] < k) {
+          const int64_t o = static_cast<int64_t>(lane + 32 * l) * list_stride + q * k + head[l];
+          hs[l] = scores[o];
+          hi[l] = widen_index(idx[o]);
+        }
+      }
+    }
+  }
+}
+
+// One warp per output row, 16-byte vectors.  Out-of-range indices produce a zero row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int64_t n_src_rows, int d,
+                   const long long* __restrict__ idx, int64_t n_idx, float* __restrict__ out) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n_idx) return;
+  const long long r = idx[i];
+  float4* dst = reinterpret_cast<float4*>(out + i * d);
+  if (r < 0 || r >= n_src_rows) {
+    for (int c = lane; c < d / 4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4* s = reinterpret_cast<const float4*>(src + r * d);
+  for (int c = lane; c < d / 4; c += 32) dst[c] = s[c];
+}
+
+}  // namespace zs

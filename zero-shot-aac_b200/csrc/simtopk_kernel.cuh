@@ -1,0 +1,328 @@
+// simtopk_kernel.cuh — the hot kernel: fused cosine-similarity GEMM + running per-query top-k.
+//
+// Replaces, for a whole batch of queries at once, what the reference does per item with
+//   torch.cosine_similarity(q, bank).topk(k)            (embeddings_related_generator.py:22)
+//   prefix @ bank.T -> softmax -> topk                   (utils.py:133-135)
+// The [Q, N] similarity matrix lives only in tensor memory (TMEM), 128 x 256 fp32 at a time.
+//
+// Shape of the contraction:  M = query rows, N = bank rows, K = embedding dim (bf16, fp32 acc).
+//   * warp 0   : TMA producer  — streams 128x64 query blocks and 256x64 bank blocks (128-byte
+//                swizzle) through a STAGES-deep shared-memory ring
+//   * warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128*CG, N=256, K=16) into one of
+//                two 256-column TMEM accumulators
+//   * warp 2   : TMEM allocator
+//   * warps 4-7: epilogue      — thread t owns query row t of the tile (TMEM lane t), reads its
+//                256 scores with tcgen05.ld and maintains a sorted top-k list in registers; the
+//                epilogue of bank tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
+// A work unit is (query tile, bank chunk); units are walked persistently with a static stride.
+// Every unit writes its k best (score, column) pairs per row; merge_lists_kernel reduces the
+// chunks.  CG == 2 pairs two CTAs of a cluster on a 256-row query tile (cta_group::2): each CTA
+// loads its own 128 query rows and half of the bank tile.
+#pragma once
+
+#include <math_constants.h>
+
+#include "ptx_sm100.cuh"
+
+namespace zs {
+
+constexpr int BLOCK_M = 128;   // query rows per CTA
+constexpr int BLOCK_N = 256;   // bank rows per accumulator tile
+constexpr int BLOCK_K = 64;    // bf16 elements per 128-byte swizzled row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512: the whole tensor memory of the SM
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_THREADS = 128;
+
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+template <int CG>
+constexpr int b_stage_bytes() { return (BLOCK_N / CG) * BLOCK_K * 2; }  // 32 KiB, or 16 KiB per CTA of a pair
+template <int CG>
+constexpr int stage_bytes() { return A_STAGE_BYTES + b_stage_bytes<CG>(); }
+constexpr int BARRIER_BYTES = 256;
+template <int CG>
+constexpr int smem_bytes() { return STAGES * stage_bytes<1>() + BARRIER_BYTES + 1024; }
+
+constexpr int IDX_SENTINEL = 0x7fffffff;
+
+// error codes written to the device flag by a timed-out wait
+enum : int { ERR_PRODUCER = 101, ERR_MMA_FULL = 102, ERR_MMA_TEMPTY = 103, ERR_EPILOGUE = 104 };
+
+struct SimTopkParams {
+  int Q;                 // query rows
+  int n_bank;            // bank rows of this shard
+  int num_k_blocks;      // d / 64
+  int num_m_tiles;       // ceil(Q / (128 * CG))
+  int num_n_tiles;       // ceil(n_bank / 256)
+  int tiles_per_chunk;   // bank tiles per work unit
+  int num_chunks;
+  int k;                 // requested list length (<= KCAP)
+  const long long* self_index;  // nullable [Q]: global bank index to skip
+  long long index_offset;       // global index of bank row 0 of this shard
+  float* part_scores;    // [num_chunks, Q, k]
+  int* part_idx;         // [num_chunks, Q, k]  column within the shard
+  float* dump;           // DUMP mode: [Q, n_bank]
+  int* err_flag;
+};
+
+// Sorted (descending score; equal scores keep arrival order = ascending column) list in registers.
+template <int KCAP>
+struct TopkList {
+  float s[KCAP];
+  int i[KCAP];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      s[j] = -CUDART_INF_F;
+      i[j] = IDX_SENTINEL;
+    }
+  }
+
+  // value at position k-1 (the admission threshold for a length-k list)
+  __device__ __forceinline__ float kth(int k) const {
+    float t = s[KCAP - 1];
+#pragma unroll
+    for (int j = 0; j < KCAP - 1; ++j)
+      if (j == k - 1) t = s[j];
+    return t;
+  }
+
+  // Insert (v, idx); precondition v > s[KCAP-1] or the element simply falls off the end.
+  __device__ __forceinline__ void insert(float v, int idx) {
+    bool gt[KCAP];
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) gt[j] = v > s[j];
+#pragma unroll
+    for (int j = KCAP - 1; j > 0; --j) {
+      s[j] = gt[j - 1] ? s[j - 1] : (gt[j] ? v : s[j]);
+      i[j] = gt[j - 1] ? i[j - 1] : (gt[j] ? idx : i[j]);
+    }
+    s[0] = gt[0] ? v : s[0];
+    i[0] = gt[0] ? idx : i[0];
+  }
+};
+
+template <int KCAP, int CG, bool DUMP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                  const __grid_constant__ CUtensorMap tmap_b, const SimTopkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base_u32 - raw_u32);
+
+  constexpr int STAGE_STRIDE = stage_bytes<1>();  // ring slot size (CG == 2 uses 32 of the 48 KiB)
+  constexpr int B_BYTES = b_stage_bytes<CG>();
+  constexpr uint32_t TX_BYTES = static_cast<uint32_t>(CG) * (A_STAGE_BYTES + B_BYTES);
+
+  const uint32_t bar_base = base_u32 + STAGES * STAGE_STRIDE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_STRIDE + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = static_cast<int>(threadIdx.x & 31);
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), NUM_EPI_THREADS * CG);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_slot), TMEM_COLS);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  // static persistent schedule: all roles walk the same unit list
+  const int worker = static_cast<int>(blockIdx.x) / CG;
+  const int num_workers = static_cast<int>(gridDim.x) / CG;
+  const int num_units = p.num_m_tiles * p.num_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t full_remote[STAGES];
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        full_remote[s] = full_bar(s);
+        if constexpr (CG == 2) {
+          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_remote[s]) : "r"(full_bar(s)));
+        }
+      }
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int m_tile = u % p.num_m_tiles;
+        const int chunk = u / p.num_m_tiles;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+        const int q_row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M;
+        for (int t = t0; t < t1; ++t) {
+          const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
+            const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            if constexpr (CG == 1) {
+              ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
+              ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+            } else {
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_remote[stage], kb * BLOCK_K, q_row);
+              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_remote[stage], kb * BLOCK_K, b_row);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t IDESC = ptx::make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_count = 0;
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int chunk = u / p.num_m_tiles;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+        for (int t = t0; t < t1; ++t, ++tile_count) {
+          const uint32_t acc = tile_count & 1u;
+          const uint32_t acc_phase = (tile_count >> 1) & 1u;
+          ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, ERR_MMA_TEMPTY);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+            ptx::tc_fence_after();
+            const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
+            const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
+            const uint64_t b_desc = ptx::make_smem_desc_sw128(a_src + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
+              ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
+                                 static_cast<uint32_t>((kb | k) != 0));
+            }
+            if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
+            else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));
+          else ptx::umma_commit_cg2(tfull_bar(acc), 0b11);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue: running top-k
+    const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) belong to this warp
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t tmem_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t tile_count = 0;
+    TopkList<KCAP> list;
+    for (int u = worker; u < num_units; u += num_workers) {
+      const int m_tile = u % p.num_m_tiles;
+      const int chunk = u / p.num_m_tiles;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+      const int row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M + row_in_tile;
+      int self_col = -1;
+      if (!DUMP && p.self_index != nullptr && row < p.Q) {
+        const long long g = p.self_index[row];
+        const long long c = g - p.index_offset;
+        if (g >= 0 && c >= 0 && c < p.n_bank) self_col = static_cast<int>(c);
+      }
+      list.init();
+      float thr = -CUDART_INF_F;
+      for (int t = t0; t < t1; ++t, ++tile_count) {
+        const uint32_t acc = tile_count & 1u;
+        const uint32_t acc_phase = (tile_count >> 1) & 1u;
+        ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, ERR_EPILOGUE);
+        ptx::tc_fence_after();
+        const int col_tile = t * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
+          ptx::tmem_ld_32x32(tmem_base + tmem_lane + acc * BLOCK_N + c0, r);
+          ptx::tmem_ld_wait();
+          const int col0 = col_tile + c0;
+          if constexpr (DUMP) {
+            if (row < p.Q) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n_bank)
+                  p.dump[static_cast<size_t>(row) * p.n_bank + col0 + j] = __uint_as_float(r[j]);
+            }
+          } else {
+            // fast path: two instructions per score, no branch
+            uint32_t cand = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (__uint_as_float(r[j]) > thr) cand |= (1u << j);
+            if (cand != 0) {
+              // rare path: spill the 32 scores to local memory so they can be indexed dynamically
+              float tmp[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(r[j]);
+              while (cand != 0) {
+                const int j = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float v = tmp[j];
+                const int col = col0 + j;
+                if (v > thr && col < p.n_bank && col != self_col) {
+                  list.insert(v, col);
+                  thr = list.kth(p.k);
+                }
+              }
+            }
+          }
+        }
+        // this thread is done with accumulator `acc`: hand it back to the MMA issuer
+        ptx::tc_fence_before();
+        if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+        else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if constexpr (!DUMP) {
+        if (row < p.Q) {
+          const size_t o = (static_cast<size_t>(chunk) * p.Q + row) * p.k;
+#pragma unroll
+          for (int j = 0; j < KCAP; ++j) {
+            if (j < p.k) {
+              p.part_scores[o + j] = list.s[j];
+              p.part_idx[o + j] = list.i[j];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+}  // namespace zs

@@ -1,0 +1,479 @@
+// zsaac_api.cu — host side of libzsaac_b200.so: the C ABI declared in include/zsaac.h.
+//
+// Owns the bf16 bank copy, the TMA descriptors and the search workspaces; picks the launch
+// geometry (bank chunks per query tile) and enqueues  normalize/cast -> fused similarity+top-k
+// -> chunk merge  on the caller's stream.  No CPU path exists: without an sm_100 device
+// zs_create fails.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/zsaac.h"
+#include "aux_kernels.cuh"
+#include "simtopk_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define ZS_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ZS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),        \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+struct zs_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cta_group = 1;           // 1, or 2 (CTA pairs, cta_group::2); env ZSAAC_CTA_GROUP overrides
+  EncodeTiledFn encode = nullptr;
+
+  __nv_bfloat16* bank = nullptr;
+  int64_t bank_rows = 0;
+  int bank_d = 0;
+  CUtensorMap bank_map;        // box {64, 256 / cta_group}
+
+  __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
+  int64_t q_ws_rows = 0;
+  float* part_scores = nullptr;   // [chunks, Q, k]
+  int* part_idx = nullptr;
+  int64_t part_elems = 0;
+  int* err_flag = nullptr;
+
+  int64_t launches = 0;
+};
+
+namespace {
+
+int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int d,
+                    int box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(zs::BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                           gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d box=%d)",
+                static_cast<int>(r), static_cast<long long>(rows), d, box_rows);
+  return ZS_OK;
+}
+
+int kcap_for(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
+
+struct Plan {
+  int m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
+};
+
+// Split the bank into `chunks` contiguous runs of 256-row tiles so that (query tiles x chunks)
+// work units fill the SMs in whole waves with the least padded work.
+Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
+  Plan pl{};
+  const int cg = ctx->cta_group;
+  const int workers = std::max(1, ctx->sm_count / cg);
+  pl.m_tiles = static_cast<int>((Q + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
+  pl.n_tiles = static_cast<int>((ctx->bank_rows + zs::BLOCK_N - 1) / zs::BLOCK_N);
+  const int max_chunks = std::min(pl.n_tiles, zs::MERGE_MAX_LISTS);
+  double best_cost = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= max_chunks; ++s) {
+    const int tpc = (pl.n_tiles + s - 1) / s;
+    const int s_eff = (pl.n_tiles + tpc - 1) / tpc;
+    if (s_eff != s) continue;  // same split as a smaller s
+    const int64_t units = static_cast<int64_t>(pl.m_tiles) * s_eff;
+    const int64_t waves = (units + workers - 1) / workers;
+    // per unit: tpc tiles + ~0.75 tile of list warm-up / pipeline fill / partial write-out
+    const double cost = static_cast<double>(waves) * (tpc + 0.75);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s_eff; }
+  }
+  pl.chunks = best_s;
+  pl.tiles_per_chunk = (pl.n_tiles + best_s - 1) / best_s;
+  const int64_t units = static_cast<int64_t>(pl.m_tiles) * pl.chunks;
+  pl.ctas = static_cast<int>(std::min<int64_t>(units, workers)) * cg;
+  return pl;
+}
+
+int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
+  if (Q > ctx->q_ws_rows) {
+    if (ctx->q_ws) { ZS_CUDA(cudaFree(ctx->q_ws)); ctx->q_ws = nullptr; ctx->q_ws_rows = 0; }
+    ZS_CUDA(cudaMalloc(&ctx->q_ws, static_cast<size_t>(Q) * ctx->bank_d * sizeof(__nv_bfloat16)));
+    ctx->q_ws_rows = Q;
+  }
+  const Plan pl = make_plan(ctx, Q, k);
+  const int64_t need = static_cast<int64_t>(pl.chunks) * Q * k;
+  if (need > ctx->part_elems) {
+    if (ctx->part_scores) { ZS_CUDA(cudaFree(ctx->part_scores)); ctx->part_scores = nullptr; }
+    if (ctx->part_idx) { ZS_CUDA(cudaFree(ctx->part_idx)); ctx->part_idx = nullptr; }
+    ctx->part_elems = 0;
+    ZS_CUDA(cudaMalloc(&ctx->part_scores, static_cast<size_t>(need) * sizeof(float)));
+    ZS_CUDA(cudaMalloc(&ctx->part_idx, static_cast<size_t>(need) * sizeof(int)));
+    ctx->part_elems = need;
+  }
+  return ZS_OK;
+}
+
+template <typename InT>
+void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int d, int normalize,
+                      cudaStream_t st) {
+  const int64_t blocks = (rows * 32 + 255) / 256;
+  zs::normalize_cast_kernel<InT, __nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      static_cast<const InT*>(in), out, rows, d, normalize);
+}
+
+template <int KCAP, int CG, bool DUMP>
+int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
+                   cudaStream_t st) {
+  auto kern = zs::zs_simtopk_kernel<KCAP, CG, DUMP>;
+  const int smem = zs::smem_bytes<CG>();
+  ZS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(zs::NUM_THREADS);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    n_attr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  ZS_CUDA(cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map, p));
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+template <int CG>
+int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
+                     bool dump, cudaStream_t st) {
+  if (dump) return launch_simtopk<8, CG, true>(ctx, qmap, p, ctas, st);
+  switch (kcap_for(p.k)) {
+    case 8: return launch_simtopk<8, CG, false>(ctx, qmap, p, ctas, st);
+    case 16: return launch_simtopk<16, CG, false>(ctx, qmap, p, ctas, st);
+    default: return launch_simtopk<32, CG, false>(ctx, qmap, p, ctas, st);
+  }
+}
+
+// Shared front half of zs_search / zs_debug_scores: cast queries, build the query map + params.
+int prepare_queries(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize,
+                    CUtensorMap* qmap, cudaStream_t st) {
+  if (q_dtype == ZS_F32) launch_normalize<float>(queries, ctx->q_ws, Q, ctx->bank_d, normalize, st);
+  else launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, ctx->bank_d, normalize, st);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return encode_rows_map(ctx, qmap, ctx->q_ws, Q, ctx->bank_d, zs::BLOCK_M);
+}
+
+}  // namespace
+
+extern "C" {
+
+int zs_abi_version(void) { return ZS_ABI_VERSION; }
+const char* zs_last_error(void) { return g_err; }
+const char* zs_kernel_name(void) { return "zs_simtopk_kernel"; }
+
+int zs_create(zs_ctx** out, int device) {
+  if (!out) return fail(ZS_ERR_INVALID, "zs_create: out is null");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(ZS_ERR_NO_DEVICE, "zs_create: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n_dev)
+    return fail(ZS_ERR_INVALID, "zs_create: device %d out of range [0, %d)", device, n_dev);
+  cudaDeviceProp prop;
+  ZS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ZS_ERR_NO_DEVICE, "zs_create: device %d is sm_%d%d; the kernels are sm_100a only",
+                device, prop.major, prop.minor);
+  zs_ctx* ctx = new (std::nothrow) zs_ctx();
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_create: out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  DeviceGuard guard(device);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return fail(ZS_ERR_CUDA, "zs_create: cuTensorMapEncodeTiled entry point not available");
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  const char* cg = getenv("ZSAAC_CTA_GROUP");
+  if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group = cg[0] - '0';
+  e = cudaMalloc(&ctx->err_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->err_flag, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(ZS_ERR_CUDA, "zs_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return ZS_OK;
+}
+
+int zs_destroy(zs_ctx* ctx) {
+  if (!ctx) return ZS_OK;
+  DeviceGuard guard(ctx->device);
+  cudaFree(ctx->bank);
+  cudaFree(ctx->q_ws);
+  cudaFree(ctx->part_scores);
+  cudaFree(ctx->part_idx);
+  cudaFree(ctx->err_flag);
+  delete ctx;
+  return ZS_OK;
+}
+
+int zs_bank_alloc(zs_ctx* ctx, int64_t n_rows, int d) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_bank_alloc: ctx is null");
+  if (n_rows < 1 || n_rows > 0x7fffff00ll)
+    return fail(ZS_ERR_INVALID, "zs_bank_alloc: n_rows=%lld outside [1, 2^31)", (long long)n_rows);
+  if (d < ZS_DIM_MULTIPLE || d > ZS_MAX_DIM || d % ZS_DIM_MULTIPLE != 0)
+    return fail(ZS_ERR_INVALID, "zs_bank_alloc: d=%d must be a multiple of %d in [%d, %d]", d,
+                ZS_DIM_MULTIPLE, ZS_DIM_MULTIPLE, ZS_MAX_DIM);
+  DeviceGuard guard(ctx->device);
+  if (ctx->bank && (ctx->bank_rows != n_rows || ctx->bank_d != d)) {
+    ZS_CUDA(cudaFree(ctx->bank));
+    ctx->bank = nullptr;
+    ctx->bank_rows = 0;
+    ctx->bank_d = 0;
+  }
+  if (ctx->bank_d != d && ctx->q_ws) {  // query workspace is sized in rows of d
+    ZS_CUDA(cudaFree(ctx->q_ws));
+    ctx->q_ws = nullptr;
+    ctx->q_ws_rows = 0;
+  }
+  if (!ctx->bank) {
+    ZS_CUDA(cudaMalloc(&ctx->bank, static_cast<size_t>(n_rows) * d * sizeof(__nv_bfloat16)));
+    ctx->bank_rows = n_rows;
+    ctx->bank_d = d;
+  }
+  return encode_rows_map(ctx, &ctx->bank_map, ctx->bank, n_rows, d, zs::BLOCK_N / ctx->cta_group);
+}
+
+int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_row, int in_dtype,
+                   int normalize, void* stream) {
+  if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_bank_upload: call zs_bank_alloc first");
+  if (!rows && n_rows > 0) return fail(ZS_ERR_INVALID, "zs_bank_upload: rows is null");
+  if (n_rows < 0 || dst_row < 0 || dst_row + n_rows > ctx->bank_rows)
+    return fail(ZS_ERR_INVALID, "zs_bank_upload: rows [%lld, %lld) outside the bank of %lld rows",
+                (long long)dst_row, (long long)(dst_row + n_rows), (long long)ctx->bank_rows);
+  if (in_dtype != ZS_F32 && in_dtype != ZS_BF16)
+    return fail(ZS_ERR_INVALID, "zs_bank_upload: unknown dtype %d", in_dtype);
+  if (n_rows == 0) return ZS_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* dst = ctx->bank + dst_row * ctx->bank_d;
+  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, ctx->bank_d, normalize, st);
+  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, ctx->bank_d, normalize, st);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+int64_t zs_bank_rows(const zs_ctx* ctx) { return ctx ? ctx->bank_rows : 0; }
+int zs_bank_dim(const zs_ctx* ctx) { return ctx ? ctx->bank_d : 0; }
+
+int zs_reserve(zs_ctx* ctx, int64_t Q, int k) {
+  if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_reserve: no bank");
+  if (Q < 1 || k < 1 || k > ZS_MAX_K) return fail(ZS_ERR_INVALID, "zs_reserve: Q=%lld k=%d", (long long)Q, k);
+  DeviceGuard guard(ctx->device);
+  return ensure_workspace(ctx, Q, k);
+}
+
+int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_chunk, int* n_ctas) {
+  if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_plan: no bank");
+  if (Q < 1) return fail(ZS_ERR_INVALID, "zs_plan: Q=%lld", (long long)Q);
+  const Plan pl = make_plan(ctx, Q, k);
+  if (n_chunks) *n_chunks = pl.chunks;
+  if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
+  if (n_ctas) *n_ctas = pl.ctas;
+  return ZS_OK;
+}
+
+int64_t zs_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, int normalize_queries,
+              const int64_t* self_index, int64_t index_offset, float* out_scores,
+              int64_t* out_indices, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_search: ctx is null");
+  if (!ctx->bank) return fail(ZS_ERR_STATE, "zs_search: no bank uploaded");
+  if (Q < 0 || Q > 0x7fffff00ll) return fail(ZS_ERR_INVALID, "zs_search: Q=%lld", (long long)Q);
+  if (q_dtype != ZS_F32 && q_dtype != ZS_BF16)
+    return fail(ZS_ERR_INVALID, "zs_search: unknown query dtype %d", q_dtype);
+  const int64_t avail = ctx->bank_rows - (self_index ? 1 : 0);
+  if (k < 1 || k > ZS_MAX_K || k > avail)
+    return fail(ZS_ERR_INVALID,
+                "zs_search: selected index k out of range (k=%d, bank rows=%lld%s, max k=%d)", k,
+                (long long)ctx->bank_rows, self_index ? " minus the excluded row" : "", ZS_MAX_K);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !out_scores || !out_indices)
+    return fail(ZS_ERR_INVALID, "zs_search: null queries / output pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_workspace(ctx, Q, k);
+  if (rc) return rc;
+  CUtensorMap qmap;
+  rc = prepare_queries(ctx, queries, Q, q_dtype, normalize_queries, &qmap, st);
+  if (rc) return rc;
+
+  const Plan pl = make_plan(ctx, Q, k);
+  zs::SimTopkParams p{};
+  p.Q = static_cast<int>(Q);
+  p.n_bank = static_cast<int>(ctx->bank_rows);
+  p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
+  p.num_m_tiles = pl.m_tiles;
+  p.num_n_tiles = pl.n_tiles;
+  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.num_chunks = pl.chunks;
+  p.k = k;
+  p.self_index = reinterpret_cast<const long long*>(self_index);
+  p.index_offset = index_offset;
+  p.part_scores = ctx->part_scores;
+  p.part_idx = ctx->part_idx;
+  p.dump = nullptr;
+  p.err_flag = ctx->err_flag;
+  rc = (ctx->cta_group == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
+                             : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  if (rc) return rc;
+
+  const int64_t blocks = (Q * 32 + 255) / 256;
+  zs::merge_lists_kernel<int><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      ctx->part_scores, ctx->part_idx, pl.chunks, Q * k, Q, k, index_offset, out_scores,
+      reinterpret_cast<long long*>(out_indices));
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t list_stride,
+             int64_t Q, int k, float* out_scores, int64_t* out_indices, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_merge: ctx is null");
+  if (S < 1 || S > zs::MERGE_MAX_LISTS)
+    return fail(ZS_ERR_INVALID, "zs_merge: S=%d outside [1, %d]", S, zs::MERGE_MAX_LISTS);
+  if (k < 1 || Q < 0 || list_stride < Q * k)
+    return fail(ZS_ERR_INVALID, "zs_merge: Q=%lld k=%d list_stride=%lld", (long long)Q, k,
+                (long long)list_stride);
+  if (Q == 0) return ZS_OK;
+  if (!scores || !indices || !out_scores || !out_indices)
+    return fail(ZS_ERR_INVALID, "zs_merge: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t blocks = (Q * 32 + 255) / 256;
+  zs::merge_lists_kernel<long long><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      scores, reinterpret_cast<const long long*>(indices), S, list_stride, Q, k, 0ll, out_scores,
+      reinterpret_cast<long long*>(out_indices));
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,
+                       const int64_t* indices, int64_t n_idx, float* out, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: ctx is null");
+  if (d < 4 || d % 4 != 0) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: d=%d must be a multiple of 4", d);
+  if (n_idx < 0 || n_src_rows < 0) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: negative size");
+  if (n_idx == 0) return ZS_OK;
+  if (!src || !indices || !out) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t blocks = (n_idx * 32 + 255) / 256;
+  zs::gather_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      src, n_src_rows, d, reinterpret_cast<const long long*>(indices), n_idx, out);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_rows, int d,
+                          void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_normalize_rows_f32: ctx is null");
+  if (d < 4 || d % 4 != 0 || n_rows < 0)
+    return fail(ZS_ERR_INVALID, "zs_normalize_rows_f32: n_rows=%lld d=%d (d must be a multiple of 4)",
+                (long long)n_rows, d);
+  if (n_rows == 0) return ZS_OK;
+  if (!in || !out) return fail(ZS_ERR_INVALID, "zs_normalize_rows_f32: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t blocks = (n_rows * 32 + 255) / 256;
+  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, d, 1);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_debug_scores(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize_queries,
+                    float* out_scores, void* stream) {
+  if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_debug_scores: no bank uploaded");
+  if (Q < 1 || !queries || !out_scores) return fail(ZS_ERR_INVALID, "zs_debug_scores: bad argument");
+  if (q_dtype != ZS_F32 && q_dtype != ZS_BF16)
+    return fail(ZS_ERR_INVALID, "zs_debug_scores: unknown query dtype %d", q_dtype);
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_workspace(ctx, Q, 1);
+  if (rc) return rc;
+  CUtensorMap qmap;
+  rc = prepare_queries(ctx, queries, Q, q_dtype, normalize_queries, &qmap, st);
+  if (rc) return rc;
+  const Plan pl = make_plan(ctx, Q, 1);
+  zs::SimTopkParams p{};
+  p.Q = static_cast<int>(Q);
+  p.n_bank = static_cast<int>(ctx->bank_rows);
+  p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
+  p.num_m_tiles = pl.m_tiles;
+  p.num_n_tiles = pl.n_tiles;
+  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.num_chunks = pl.chunks;
+  p.k = 1;
+  p.dump = out_scores;
+  p.err_flag = ctx->err_flag;
+  return (ctx->cta_group == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, true, st)
+                               : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, true, st);
+}
+
+}  // extern "C"

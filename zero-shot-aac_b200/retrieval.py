@@ -1,0 +1,254 @@
+"""Related-caption retrieval on one B200: cosine similarity against a caption-embedding bank and
+per-query top-k, through the C ABI of libzsaac_b200.so.
+
+`related_topk` is the batched form of what the reference computes one item at a time in
+process_data (data_handing/embeddings_related_generator.py:21-22):
+
+    text_embs = F.normalize(item['text_embedding'], dim=-1).to('cuda')
+    ids = torch.cosine_similarity(text_embs, valid_text_embs).topk(topnumber)[1]
+
+and of utils.sound_effect_choice (utils.py:133-135, no normalisation there).  torch is used for
+device memory and streams only; every kernel on the path lives in the native library.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _abi
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "zsaac_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback for the "
+            "related-caption retrieval path")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _abi.ZS_F32
+    if t.dtype == torch.bfloat16:
+        return _abi.ZS_BF16
+    raise TypeError(f"embeddings must be float32 or bfloat16, got {t.dtype}")
+
+
+class RelatedBank:
+    """A caption-embedding memory bank resident on one GPU as bf16 rows (library-owned copy).
+
+    rows         number of bank rows held by this object (a shard when index_offset > 0)
+    dim          embedding dimension (multiple of 64; 1024 in the reference)
+    index_offset global index of local row 0; added to every index `search` returns
+    """
+
+    def __init__(self, rows: int, dim: int, *, device=None, index_offset: int = 0):
+        _require_cuda()
+        self._lib = _abi.load_library()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError(f"RelatedBank lives on a CUDA device, got {dev}")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.rows = int(rows)
+        self.dim = int(dim)
+        self.index_offset = int(index_offset)
+        handle = ctypes.c_void_p()
+        _abi.check(self._lib.zs_create(ctypes.byref(handle), dev.index))
+        self._ctx = handle
+        self._finalizer = weakref.finalize(self, self._lib.zs_destroy, handle)
+        _abi.check(self._lib.zs_bank_alloc(self._ctx, self.rows, self.dim))
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_tensor(cls, bank: torch.Tensor, *, normalize: bool = True, index_offset: int = 0,
+                    device=None) -> "RelatedBank":
+        """Build from a [N, d] float32 / bfloat16 tensor (moved to the GPU if it is not there)."""
+        if bank.dim() != 2:
+            raise ValueError(f"bank must be [N, d], got {tuple(bank.shape)}")
+        _require_cuda()
+        if not bank.is_cuda:
+            bank = bank.to(device if device is not None else "cuda", non_blocking=False)
+        obj = cls(bank.shape[0], bank.shape[1], device=bank.device, index_offset=index_offset)
+        obj.upload(bank, 0, normalize=normalize)
+        return obj
+
+    def upload(self, rows: torch.Tensor, dst_row: int = 0, *, normalize: bool = True) -> None:
+        """Cast (and L2-normalise, F.normalize eps=1e-12) `rows` into bank rows [dst_row, ...)."""
+        if rows.dim() != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")
+        rows = rows.detach()
+        if rows.device != self.device:
+            rows = rows.to(self.device)
+        rows = rows.contiguous()
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_bank_upload(
+                self._ctx, rows.data_ptr(), rows.shape[0], int(dst_row), _dtype_code(rows),
+                1 if normalize else 0, _stream_ptr(self.device)))
+        # `rows` must stay alive until the enqueued kernel has read it
+        rows.record_stream(torch.cuda.current_stream(self.device))
+
+    # ------------------------------------------------------------------ search
+    def reserve(self, n_queries: int, k: int) -> None:
+        _abi.check(self._lib.zs_reserve(self._ctx, int(n_queries), int(k)))
+
+    def search(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
+               self_index: Optional[torch.Tensor] = None,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top-k of every query against this bank.
+
+        queries [Q, d] float32 / bfloat16 on this device.  Returns (scores [Q, k] float32
+        descending, indices [Q, k] int64 global), ties ordered by ascending index.
+        self_index: optional [Q] int64 global bank index each query must not return.
+        """
+        if queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {tuple(queries.shape)}")
+        if queries.device != self.device:
+            raise ValueError(f"queries are on {queries.device}, the bank is on {self.device}")
+        k = int(k)
+        queries = queries.detach().contiguous()
+        q = queries.shape[0]
+        if out is None:
+            scores = torch.empty((q, k), dtype=torch.float32, device=self.device)
+            indices = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        else:
+            scores, indices = out
+            if (scores.shape != (q, k) or indices.shape != (q, k) or scores.dtype != torch.float32
+                    or indices.dtype != torch.int64 or not scores.is_contiguous()
+                    or not indices.is_contiguous()):
+                raise ValueError("out must be contiguous (float32 [Q,k], int64 [Q,k])")
+        self_ptr = None
+        if self_index is not None:
+            self_index = self_index.detach().to(device=self.device, dtype=torch.int64).contiguous()
+            if self_index.shape != (q,):
+                raise ValueError(f"self_index must be [{q}], got {tuple(self_index.shape)}")
+            self_ptr = self_index.data_ptr()
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_search(
+                self._ctx, queries.data_ptr(), q, _dtype_code(queries), k,
+                1 if normalize_queries else 0, self_ptr, self.index_offset,
+                scores.data_ptr(), indices.data_ptr(), _stream_ptr(self.device)))
+        return scores, indices
+
+    def debug_scores(self, queries: torch.Tensor, *, normalize_queries: bool = True) -> torch.Tensor:
+        """Full [Q, rows] similarity matrix out of the same tcgen05 pipeline (tests only)."""
+        queries = queries.detach().contiguous()
+        out = torch.empty((queries.shape[0], self.rows), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_debug_scores(
+                self._ctx, queries.data_ptr(), queries.shape[0], _dtype_code(queries),
+                1 if normalize_queries else 0, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ helpers on the same ctx
+    def merge(self, scores: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """k-way merge of [S, Q, k] sorted lists -> [Q, k] under (score desc, index asc)."""
+        if scores.dim() != 3 or scores.shape != indices.shape:
+            raise ValueError("merge expects scores and indices of identical shape [S, Q, k]")
+        s, q, k = scores.shape
+        scores = scores.to(torch.float32).contiguous()
+        indices = indices.to(torch.int64).contiguous()
+        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_merge(
+                self._ctx, scores.data_ptr(), indices.data_ptr(), s, q * k, q, k,
+                out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(self.device)))
+        return out_s, out_i
+
+    def gather_rows(self, src: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+        """src[indices] for a float32 [N, d] tensor on this device -> [*indices.shape, d]."""
+        if src.dtype != torch.float32 or src.dim() != 2 or src.device != self.device:
+            raise ValueError("gather_rows expects a float32 [N, d] tensor on the bank's device")
+        src = src.contiguous()
+        flat = indices.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
+        out = torch.empty((flat.numel(), src.shape[1]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_gather_rows_f32(
+                self._ctx, src.data_ptr(), src.shape[0], src.shape[1], flat.data_ptr(),
+                flat.numel(), out.data_ptr(), _stream_ptr(self.device)))
+        return out.view(*indices.shape, src.shape[1])
+
+    def normalize_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """F.normalize(x, dim=-1) for a float32 [N, d] tensor on this device (new tensor)."""
+        if x.dtype != torch.float32 or x.dim() != 2 or x.device != self.device:
+            raise ValueError("normalize_rows expects a float32 [N, d] tensor on the bank's device")
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_normalize_rows_f32(
+                self._ctx, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                _stream_ptr(self.device)))
+        return out
+
+    def plan(self, n_queries: int, k: int) -> Tuple[int, int, int]:
+        """(bank chunks, 256-row tiles per chunk, CTAs) the library would launch."""
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _abi.check(self._lib.zs_plan(self._ctx, int(n_queries), int(k), ctypes.byref(a),
+                                     ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.zs_launch_count(self._ctx))
+
+    def close(self) -> None:
+        self._finalizer()
+
+
+# ------------------------------------------------------------------------------------------------
+# Bank cache: process_data / sound_effect_choice receive the fp32 bank tensor on every call, as
+# in the reference; the bf16 copy is rebuilt only when that tensor (identity, version) changes.
+_BANK_CACHE: "dict[tuple, tuple]" = {}   # key -> (weakref to the source tensor, RelatedBank)
+_BANK_CACHE_MAX = 4
+
+
+def bank_for(bank: torch.Tensor, *, normalize: bool) -> RelatedBank:
+    key = (bank.data_ptr(), tuple(bank.shape), bank.dtype, str(bank.device), bank._version,
+           bool(normalize))
+    hit = _BANK_CACHE.get(key)
+    if hit is not None and hit[0]() is bank:
+        return hit[1]
+    if hit is not None:                      # same address, different tensor object: stale
+        _BANK_CACHE.pop(key)[1].close()
+    obj = RelatedBank.from_tensor(bank, normalize=normalize)
+    if len(_BANK_CACHE) >= _BANK_CACHE_MAX:
+        _BANK_CACHE.pop(next(iter(_BANK_CACHE)))[1].close()
+    _BANK_CACHE[key] = (weakref.ref(bank), obj)
+    return obj
+
+
+def clear_bank_cache() -> None:
+    while _BANK_CACHE:
+        _BANK_CACHE.popitem()[1][1].close()
+
+
+def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_self: bool = False,
+                 self_index: Optional[torch.Tensor] = None, normalize: bool = True
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """scores, indices = top-k of cosine_similarity(queries, bank).
+
+    queries [Q, d], bank [N, d] (float32 or bfloat16).  With normalize=True both sides are
+    L2-normalised first (cosine similarity, reference embeddings_related_generator.py:21-22);
+    with normalize=False the raw dot product is ranked (reference utils.py:133).
+    exclude_self=True drops bank row i from the result of query i (self_index defaults to
+    arange(Q)); the reference itself never excludes (slot 0 of its output is the item).
+    Returns float32 [Q, k] scores (descending) and int64 [Q, k] bank indices on the GPU.
+    """
+    _require_cuda()
+    rb = bank_for(bank, normalize=normalize)   # a CPU bank is copied to the current GPU once
+    q = queries.detach()
+    if q.dim() == 1:
+        q = q.unsqueeze(0)
+    q = q.to(rb.device)
+    if exclude_self and self_index is None:
+        self_index = torch.arange(q.shape[0], dtype=torch.int64, device=rb.device)
+    return rb.search(q, k, normalize_queries=normalize, self_index=self_index)
