@@ -103,10 +103,13 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k,
 
 /* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
  * bank chunks) under the total order (score desc, index asc).
- *   scores  list s of query q starts at scores  + s*list_stride + q*k   (elements)
- *   indices likewise.  Output [Q, k].  Stand-alone: needs no bank. */
-int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t list_stride,
-             int64_t Q, int k, float* out_scores, int64_t* out_indices, void* stream);
+ *   scores  list s of query q starts at scores  + s*score_stride + q*k   (float elements)
+ *   indices list s of query q starts at indices + s*index_stride + q*k   (int64 elements)
+ * (two strides so that one all-gathered byte buffer holding [scores | indices] per rank can be
+ * merged in place).  Output [Q, k].  Stand-alone: needs no bank. */
+int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t score_stride,
+             int64_t index_stride, int64_t Q, int k, float* out_scores, int64_t* out_indices,
+             void* stream);
 
 /* Gather rows: out[i, :] = src[indices[i], :] for fp32 [*, d] row-major src (replaces
  * `valid_text_embs[ids]`, reference embeddings_related_generator.py:23). */
@@ -121,6 +124,14 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t zs_launch_count(const zs_ctx* ctx);
+
+/* Per-launch device timing of the fused similarity+top-k kernel.  With enable != 0 every
+ * zs_search brackets that kernel with CUDA events on the caller's stream (a ring of
+ * ZS_PROFILE_RING launches; enabling resets the ring).  zs_profile_read synchronises on the
+ * recorded events and returns the durations in milliseconds, oldest first. */
+#define ZS_PROFILE_RING 256
+int zs_profile_enable(zs_ctx* ctx, int enable);
+int zs_profile_read(zs_ctx* ctx, float* ms_out, int max_entries, int* n_entries);
 
 /* Test hook: run the same TMA + tcgen05 pipeline but write the full fp32 score matrix
  * [Q, n_bank] (row-major) instead of the top-k.  Small shapes only. */

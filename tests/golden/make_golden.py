@@ -1,0 +1,163 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own functions (build container only).
+
+Imports data_handing/embeddings_related_generator{,_wavcaps}.py and utils.sound_effect_choice
+from /root/reference unmodified; the only shim maps the hard-coded 'cuda' device
+(embeddings_related_generator.py:15,21) to 'cpu' because the build container has no GPU.
+/root/reference does not exist on the GPU box, so the outputs are committed as small fixtures:
+inputs are stored as seeds (numpy RandomState streams are frozen by numpy's compatibility
+policy) and outputs as indices + scores + per-row float64 checksums.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+"""
+import importlib.util
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+D = 1024
+
+
+def load_ref_module(rel_path, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel_path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class cuda_to_cpu:
+    """Route Tensor.to('cuda') to the CPU for the duration of the block."""
+
+    def __enter__(self):
+        self._orig = torch.Tensor.to
+
+        def to(t, *a, **kw):
+            a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+            if isinstance(kw.get("device"), str) and kw["device"].startswith("cuda"):
+                kw["device"] = "cpu"
+            return self._orig(t, *a, **kw)
+
+        torch.Tensor.to = to
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.to = self._orig
+
+
+# ---- input recipes (shared with tests/fixtures.py: keep in sync) -----------------------------
+def make_embeddings(case):
+    rs = np.random.RandomState(case["seed"])
+    n = case["n"]
+    if case["dist"] == "gauss":
+        x = rs.standard_normal((n, D)).astype(np.float32)
+    elif case["dist"] == "clustered":
+        centres = rs.standard_normal((case["centres"], D)).astype(np.float32)
+        assign = rs.randint(0, case["centres"], size=n)
+        x = centres[assign] + case["sigma"] * rs.standard_normal((n, D)).astype(np.float32)
+    else:
+        raise ValueError(case["dist"])
+    x = x * (0.5 + rs.rand(n, 1).astype(np.float32) * 4.0)   # rows are NOT unit norm on input
+    for (dst, src) in case.get("duplicates", []):
+        x[dst] = x[src]
+    return x
+
+
+CASES = {
+    "generator_gauss": dict(seed=1001, n=64, k=5, dist="gauss", files=[64], module="single"),
+    "generator_clustered": dict(seed=1002, n=96, k=5, dist="clustered", centres=8, sigma=0.05,
+                                files=[96], module="single"),
+    "wavcaps_multi_dup": dict(seed=1003, n=72, k=3, dist="gauss", files=[40, 24, 8],
+                              duplicates=[(50, 7), (71, 7)], module="wavcaps"),
+    "generator_k1": dict(seed=1004, n=33, k=1, dist="gauss", files=[33], module="single"),
+}
+
+
+def run_generator_case(name, case):
+    mod = load_ref_module(
+        "data_handing/embeddings_related_generator.py" if case["module"] == "single"
+        else "data_handing/embeddings_related_generator_wavcaps.py", "ref_gen_" + name)
+    x = make_embeddings(case)
+    records = [{"caption": f"caption number {i} of the synthetic set", "text_id": i,
+                "text_embedding": torch.from_numpy(x[i:i + 1].copy())} for i in range(case["n"])]
+    tmp = tempfile.mkdtemp()
+    paths, lo = [], 0
+    for fi, cnt in enumerate(case["files"]):
+        p = os.path.join(tmp, f"in{fi}.pkl")
+        with open(p, "wb") as f:
+            pickle.dump(records[lo:lo + cnt], f)
+        paths.append(p)
+        lo += cnt
+    out_path = os.path.join(tmp, "out_related.pkl")
+    with cuda_to_cpu():
+        bank, all_data = mod.load_data(paths[0] if case["module"] == "single" else paths)
+        gen = mod.process_data(bank, all_data, case["k"])
+        mod.save_data_to_hdf5(gen, out_path, len(all_data))
+    # read back with the reader loop of dataset/dataset.py:64-78 (restated; that module does not
+    # import under transformers 5.x)
+    items = []
+    with open(out_path, "rb") as f:
+        while True:
+            try:
+                it = pickle.load(f)
+                items.extend(it) if isinstance(it, list) else items.append(it)
+            except EOFError:
+                break
+    assert len(items) == case["n"]
+    xn = torch.nn.functional.normalize(torch.from_numpy(x), dim=-1)
+    rel_idx = np.zeros((case["n"], case["k"]), np.int64)
+    rel_score = np.zeros((case["n"], case["k"]), np.float32)
+    rel_rowsum = np.zeros((case["n"], case["k"]), np.float64)
+    for i, it in enumerate(items):
+        rel = it["related_embeddings"]
+        assert rel.shape == (case["k"], D) and rel.dtype == torch.float32 and rel.device.type == "cpu"
+        assert it["text_id"] == i and set(it.keys()) == {"caption", "text_id", "text_embedding",
+                                                         "related_embeddings"}
+        sim = rel @ xn.T                       # which input row is each related row?
+        rel_idx[i] = sim.argmax(dim=1).numpy()
+        rel_score[i] = (xn[i:i + 1] @ rel.T).numpy()[0]
+        rel_rowsum[i] = rel.double().sum(dim=1).numpy()
+    # bank order the reference's set() produced, expressed as input indices
+    order = (bank @ xn.T).argmax(dim=1).numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), related_index=rel_idx,
+                        related_score=rel_score, related_rowsum=rel_rowsum, bank_order=order,
+                        bank_rowsum=bank.double().sum(dim=1).numpy())
+    print(f"{name}: n={case['n']} k={case['k']} top1==self {float((rel_idx[:, 0] == np.arange(case['n'])).mean()):.3f}")
+
+
+SEC_CASES = {
+    "sound_effect_q1": dict(seed=2001, q=1, labels=527, k=3),
+    "sound_effect_q4": dict(seed=2002, q=4, labels=527, k=5),
+}
+
+
+def make_sec_inputs(case):
+    rs = np.random.RandomState(case["seed"])
+    bank = rs.standard_normal((case["labels"], D)).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    prefix = rs.standard_normal((case["q"], D)).astype(np.float32)
+    prefix /= np.linalg.norm(prefix, axis=1, keepdims=True)
+    return prefix, bank
+
+
+def run_sec_case(name, case):
+    sys.path.insert(0, REF)
+    import utils as ref_utils   # /root/reference/utils.py (imports models.caption_model)
+    prefix, bank = make_sec_inputs(case)
+    idx = ref_utils.sound_effect_choice(torch.from_numpy(prefix), torch.from_numpy(bank), case["k"])
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (case["q"], case["k"])
+    sim = torch.from_numpy(prefix) @ torch.from_numpy(bank).T
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), index=idx.numpy(),
+                        score=sim.gather(1, idx).numpy())
+    print(f"{name}: index[0]={idx[0].tolist()}")
+
+
+if __name__ == "__main__":
+    for n, c in CASES.items():
+        run_generator_case(n, c)
+    for n, c in SEC_CASES.items():
+        run_sec_case(n, c)

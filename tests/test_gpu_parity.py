@@ -1,0 +1,283 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes), against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): scores within 1e-3 absolute of the fp32 oracle (the kernel
+multiplies bf16-rounded operands with fp32 accumulation); index sets identical except at
+near-ties (oracle score gap < 1e-3); shard merge bit-exact with the single-bank result.
+"""
+import os
+
+import pytest
+import torch
+
+import helpers
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3     # north_star: |score - fp32 reference| <= 1e-3
+BF16_TOL = 1e-4      # against the same product of bf16-rounded operands: accumulation order only
+
+
+@pytest.fixture(scope="module")
+def zs():
+    import zsaac_b200
+    assert torch.cuda.is_available()
+    zsaac_b200.load_library()          # fails loudly if the extension is missing
+    return zsaac_b200
+
+
+@pytest.fixture(params=["1", "2", "auto"])
+def cta_group(request, monkeypatch):
+    if request.param == "auto":
+        monkeypatch.delenv("ZSAAC_CTA_GROUP", raising=False)
+    else:
+        monkeypatch.setenv("ZSAAC_CTA_GROUP", request.param)
+    return request.param
+
+
+def bf16_scores(q, b, normalize=True):
+    if normalize:
+        q = torch.nn.functional.normalize(q.float(), dim=-1)
+        b = torch.nn.functional.normalize(b.float(), dim=-1)
+    return q.bfloat16().float() @ b.bfloat16().float().T
+
+
+def run_search(zs, q, b, k, **kw):
+    rb = zs.RelatedBank.from_tensor(b.cuda(), normalize=kw.pop("normalize", True))
+    try:
+        s, i = rb.search(q.cuda(), k, **kw)
+        torch.cuda.synchronize()
+        return s.cpu(), i.cpu()
+    finally:
+        rb.close()
+
+
+# ------------------------------------------------------------------------------------------ scores
+@pytest.mark.parametrize("Q,N,d", [(128, 256, 64), (1, 257, 1024), (300, 1000, 1024),
+                                   (129, 255, 1024), (257, 513, 512), (1045, 19195, 1024)])
+def test_score_matrix_matches_oracle(zs, cta_group, Q, N, d):
+    q, b = helpers.seeded((Q, d), Q + N), helpers.seeded((N, d), Q * N + 1)
+    rb = zs.RelatedBank.from_tensor(b.cuda())
+    got = rb.debug_scores(q.cuda()).cpu()
+    rb.close()
+    assert (got - bf16_scores(q, b)).abs().max().item() < BF16_TOL
+    exact = torch.from_numpy(oracle.exact_scores(q, b)).float()
+    assert (got - exact).abs().max().item() < SCORE_TOL
+
+
+# ------------------------------------------------------------------------------------------ top-k
+SHAPES = [
+    # Q, N, k
+    (1045, 19195, 5),     # BASELINE config 1: Clotho eval
+    (975, 49838, 10),     # BASELINE config 2: AudioCaps
+    (1, 527, 3),          # one query vs an AudioSet-label-sized bank
+    (3, 255, 1),          # single partial tile, k = 1
+    (130, 256, 32),       # k = ZS_MAX_K, exact tile multiple, 2 query tiles
+    (257, 70001, 17),     # ragged everywhere
+    (64, 40, 32),         # k close to N
+    (33, 33, 32),         # k = N - 1
+]
+
+
+@pytest.mark.parametrize("Q,N,k", SHAPES)
+def test_topk_matches_oracle(zs, cta_group, Q, N, k):
+    q, b = helpers.seeded((Q, 1024), 3 * Q + N + k), helpers.seeded((N, 1024), 5 * N + k)
+    s, i = run_search(zs, q, b, k)
+    rep = oracle.check_topk(s, i, q, b, k, score_tol=SCORE_TOL, tie_tol=1e-3)
+    assert rep["ok"], rep
+    # against identically rounded operands the result must be exact (no ties in Gaussian data)
+    ws, wi = oracle.stable_topk(bf16_scores(q, b), k)
+    assert (s - ws).abs().max().item() < BF16_TOL
+    assert (i == wi).float().mean().item() > 0.999
+
+
+def test_k_equals_n(zs, cta_group):
+    q, b = helpers.seeded((5, 1024), 1), helpers.seeded((20, 1024), 2)
+    s, i = run_search(zs, q, b, 20)
+    assert torch.equal(torch.sort(i, dim=1).values, torch.arange(20).expand(5, 20))
+    assert oracle.check_topk(s, i, q, b, 20)["ok"]
+
+
+def test_clustered_bank_near_ties(zs, cta_group):
+    b = helpers.clustered(20000, 1024, 512, 0.05, 11)
+    q = b[torch.randperm(20000, generator=torch.Generator().manual_seed(1))[:300]] \
+        + 0.01 * helpers.seeded((300, 1024), 12)
+    s, i = run_search(zs, q, b, 10)
+    rep = oracle.check_topk(s, i, q, b, 10, score_tol=SCORE_TOL, tie_tol=1e-3)
+    assert rep["ok"], rep
+
+
+def test_duplicate_rows_tie_order_is_ascending_index(zs, cta_group):
+    b = helpers.seeded((3000, 1024), 21)
+    for dst in (17, 700, 2999):
+        b[dst] = b[4]                                   # 4 identical rows across tiles / chunks
+    q = b[4:5].clone()
+    s, i = run_search(zs, q, b, 6)
+    assert i[0, :4].tolist() == [4, 17, 700, 2999]
+    assert s[0, 0] == s[0, 1] == s[0, 2] == s[0, 3]
+
+
+def test_zero_norm_rows_and_queries(zs):
+    b = helpers.seeded((600, 1024), 31)
+    b[100] = 0.0                                        # F.normalize eps: stays the zero vector
+    q = helpers.seeded((4, 1024), 32)
+    q[2] = 0.0
+    s, i = run_search(zs, q, b, 5)
+    assert torch.isfinite(s).all()
+    assert (s[2] == 0).all()                            # zero query: every similarity is 0
+    assert i[2].tolist() == [0, 1, 2, 3, 4]             # all tied -> ascending index
+    rep = oracle.check_topk(s[[0, 1, 3]], i[[0, 1, 3]], q[[0, 1, 3]], b, 5)
+    assert rep["ok"], rep
+
+
+def test_bf16_inputs_and_unnormalised_dot_product(zs):
+    q = torch.nn.functional.normalize(helpers.seeded((70, 1024), 41), dim=-1)
+    b = torch.nn.functional.normalize(helpers.seeded((5000, 1024), 42), dim=-1)
+    s32, i32 = run_search(zs, q, b, 8, normalize=False, normalize_queries=False)
+    s16, i16 = run_search(zs, q.bfloat16(), b.bfloat16(), 8, normalize=False, normalize_queries=False)
+    assert torch.equal(i32, i16) and torch.equal(s32, s16)     # same bf16 operands either way
+    assert oracle.check_topk(s32, i32, q, b, 8, normalize=False)["ok"]
+    # raw dot product of un-normalised data: ranking by q.b, not by cosine
+    q2, b2 = helpers.seeded((9, 64), 43) * 3.0, helpers.seeded((900, 64), 44) * 0.5
+    s, i = run_search(zs, q2, b2, 4, normalize=False, normalize_queries=False)
+    ref = q2.bfloat16().float() @ b2.bfloat16().float().T
+    ws, wi = oracle.stable_topk(ref, 4)
+    assert torch.equal(i, wi) and (s - ws).abs().max() < 1e-3 * ws.abs().max()
+
+
+def test_self_exclusion(zs, cta_group):
+    b = helpers.seeded((5000, 1024), 51)
+    q = b[:300] + 0.02 * helpers.seeded((300, 1024), 52)
+    self_index = torch.arange(300)
+    s0, i0 = run_search(zs, q, b, 5)
+    assert (i0[:, 0] == self_index).all()                     # reference behaviour: top-1 = itself
+    s, i = run_search(zs, q, b, 5, self_index=self_index.cuda())
+    assert not (i == self_index[:, None]).any()
+    assert oracle.check_topk(s, i, q, b, 5, self_index=self_index)["ok"]
+    assert torch.equal(i[:, :4], i0[:, 1:]) and torch.equal(s[:, :4], s0[:, 1:])
+    # negative entries mean "no exclusion"
+    mixed = self_index.clone()
+    mixed[::2] = -1
+    s2, i2 = run_search(zs, q, b, 5, self_index=mixed.cuda())
+    assert torch.equal(i2[::2], i0[::2]) and torch.equal(i2[1::2], i[1::2])
+
+
+# ------------------------------------------------------------------------------ shard-merge exactness
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shard_merge_is_bit_exact(zs, cta_group, world):
+    """Bank split into `world` row ranges on ONE GPU (shards are just row ranges): merged result
+    must be bit-identical to the single-bank result."""
+    from zsaac_b200.sharded import shard_bounds
+    N, Q, k = 30011, 500, 32
+    b = helpers.clustered(N, 1024, 300, 0.08, 61).cuda()
+    b[N // 2 + 1] = b[10]                                        # tie across a shard boundary
+    q = (b[:Q] + 0.05 * helpers.seeded((Q, 1024), 62).cuda()).contiguous()
+    whole = zs.RelatedBank.from_tensor(b)
+    s1, i1 = whole.search(q, k)
+    parts_s, parts_i = [], []
+    for lo, hi in shard_bounds(N, world):
+        shard = zs.RelatedBank.from_tensor(b[lo:hi], index_offset=lo)
+        s, i = shard.search(q, k)
+        parts_s.append(s)
+        parts_i.append(i)
+        torch.cuda.synchronize()
+        shard.close()
+    ms, mi = whole.merge(torch.stack(parts_s), torch.stack(parts_i))
+    torch.cuda.synchronize()
+    assert torch.equal(mi, i1) and torch.equal(ms, s1)
+    os_, oi = oracle.merge_lists(torch.stack(parts_s).cpu(), torch.stack(parts_i).cpu())
+    assert torch.equal(oi, mi.cpu()) and torch.equal(os_, ms.cpu())
+    whole.close()
+
+
+def test_merge_strided_views_and_validation(zs):
+    rb = zs.RelatedBank(256, 64)
+    S, Q, k = 3, 11, 4
+    raw = torch.sort(helpers.seeded((S, Q, k), 71), dim=2, descending=True).values.cuda()
+    idx = torch.stack([torch.arange(k) + 100 * s for s in range(S)]).unsqueeze(1).expand(S, Q, k).contiguous().cuda()
+    pad_s = torch.zeros(S, Q * k + 6, device="cuda")
+    pad_s[:, :Q * k] = raw.view(S, -1)
+    ms, mi = rb.merge(pad_s[:, :Q * k].view(S, Q, k), idx)
+    os_, oi = oracle.merge_lists(raw.cpu(), idx.cpu())
+    assert torch.equal(ms.cpu(), os_) and torch.equal(mi.cpu(), oi)
+    with pytest.raises(ValueError):
+        rb.merge(raw, idx[:, :, :2])
+    rb.close()
+
+
+# ------------------------------------------------------------------------------------ error behaviour
+def test_argument_errors_raise(zs):
+    b = helpers.seeded((40, 1024), 81).cuda()
+    rb = zs.RelatedBank.from_tensor(b)
+    q = helpers.seeded((2, 1024), 82).cuda()
+    with pytest.raises(RuntimeError, match="out of range"):     # torch.topk wording
+        rb.search(q, 41)
+    with pytest.raises(RuntimeError, match="out of range"):
+        rb.search(q, 33)                                        # > ZS_MAX_K
+    with pytest.raises(RuntimeError, match="out of range"):
+        rb.search(q, 0)
+    with pytest.raises(RuntimeError, match="out of range"):
+        rb.search(q, 40, self_index=torch.zeros(2, dtype=torch.int64).cuda())
+    with pytest.raises(ValueError):
+        rb.search(q[:, :512], 3)
+    with pytest.raises(TypeError):
+        rb.search(q.half(), 3)
+    with pytest.raises(ValueError):
+        rb.search(q.cpu(), 3)
+    s, i = rb.search(q[:0], 3)                                  # empty batch is a no-op
+    assert s.shape == (0, 3) and i.shape == (0, 3)
+    rb.close()
+    with pytest.raises(RuntimeError):
+        zs.RelatedBank(10, 1000)                                # d not a multiple of 64
+
+
+def test_normalize_and_gather_kernels(zs):
+    x = helpers.seeded((1000, 1024), 91) * 7.0
+    x[3] = 0.0
+    rb = zs.RelatedBank(1, 1024)
+    got = rb.normalize_rows(x.cuda()).cpu()
+    want = oracle.normalize_rows(x)
+    assert (got - want).abs().max().item() < 1e-6
+    idx = torch.tensor([[5, 0, 999], [3, 3, 17]])
+    g = rb.gather_rows(got.cuda(), idx.cuda()).cpu()
+    assert torch.equal(g, got[idx])
+    rb.close()
+
+
+# --------------------------------------------------------- full-size, size-independent properties
+def test_wavcaps_scale_properties(zs):
+    """BASELINE config 3 size (8192 x 400k, k=10): checked through properties, not a full oracle."""
+    N, Q, k = 400_000, 8192, 10
+    g = torch.Generator(device="cuda").manual_seed(103)
+    b = torch.randn(N, 1024, device="cuda", generator=g)
+    q = torch.randn(Q, 1024, device="cuda", generator=g)
+    planted = torch.randperm(N, device="cuda", generator=g)[:Q]
+    q[:4096] = b[planted[:4096]] + 0.3 * q[:4096]               # first half: a known nearest row
+    rb = zs.RelatedBank.from_tensor(b)
+    s, i = rb.search(q, k)
+    s2, i2 = rb.search(q, k)
+    torch.cuda.synchronize()
+    assert torch.equal(s, s2) and torch.equal(i, i2)            # deterministic / idempotent
+    assert (i[:4096, 0] == planted[:4096]).all()                # planted neighbour is top-1
+    assert (s[:, 1:] <= s[:, :-1]).all() and ((i >= 0) & (i < N)).all()
+    assert (torch.sort(i, dim=1).values.diff(dim=1) != 0).all()
+    # positive scaling of queries / bank rows cannot change a cosine ranking
+    s3, i3 = rb.search(q * 3.5, k)
+    assert (i3 == i).float().mean().item() > 0.999 and (s3 - s).abs().max().item() < 1e-3
+    # bank permutation: same scores bit for bit, indices mapped through the permutation
+    perm = torch.randperm(N, device="cuda", generator=g)
+    rbp = zs.RelatedBank.from_tensor(b[perm])
+    sp, ip = rbp.search(q[:1024], k)
+    torch.cuda.synchronize()
+    assert torch.equal(sp, s[:1024])
+    mism = perm[ip] != i[:1024]
+    tie = torch.zeros_like(mism)
+    eq = s[:1024, 1:] == s[:1024, :-1]
+    tie[:, 1:] |= eq
+    tie[:, :-1] |= eq
+    assert not (mism & ~tie).any()            # indices may only differ inside exact score ties
+    # a 512-query slice against the fp32 oracle
+    rep = oracle.check_topk(s[4000:4512].cpu(), i[4000:4512].cpu(), q[4000:4512].cpu(), b.cpu(), k)
+    assert rep["ok"], rep
+    rb.close()
+    rbp.close()

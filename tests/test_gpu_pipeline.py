@@ -1,0 +1,149 @@
+"""GPU (-m gpu): the reference-facing Python surface (load_data / process_data /
+save_data_to_hdf5 / main, sound_effect_choice) against the golden vectors produced by the
+reference's own functions, and the output-file contract of dataset/dataset.py:64-78."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import recipes
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _modules():
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.data_handing import embeddings_related_generator as single
+    from zsaac_b200.data_handing import embeddings_related_generator_wavcaps as multi
+    return single, multi
+
+
+@pytest.mark.parametrize("name", list(recipes.CASES))
+def test_generator_matches_reference_golden(name, tmp_path):
+    case = recipes.CASES[name]
+    single, multi = _modules()
+    mod = single if case["module"] == "single" else multi
+    x, recs = helpers.case_records(case)
+    paths = helpers.write_case_files(case, recs, tmp_path)
+    g = helpers.golden(name)
+
+    bank, all_data = mod.load_data(paths[0] if case["module"] == "single" else paths)
+    assert bank.is_cuda and bank.dtype == torch.float32 and tuple(bank.shape) == (case["n"], helpers.D)
+    assert len(all_data) == case["n"]
+    # bank rows equal the reference's F.normalize output (its set() order is a permutation)
+    np.testing.assert_allclose(bank.double().sum(dim=1).cpu().numpy()[g["bank_order"]],
+                               g["bank_rowsum"], atol=1e-5)
+    assert (bank.norm(dim=1) - 1).abs().max().item() < 1e-6
+
+    out_path = str(tmp_path / "out_related.pkl")
+    gen = mod.process_data(bank, all_data, case["k"])
+    assert iter(gen) is gen                                     # lazy generator, like the reference
+    mod.save_data_to_hdf5(gen, out_path, len(all_data))
+
+    items = helpers.read_related_stream(out_path)
+    assert len(items) == case["n"]
+    xn = torch.nn.functional.normalize(torch.from_numpy(x), dim=-1)
+    exact = oracle.exact_scores(torch.from_numpy(x), torch.from_numpy(x))
+    bank_cpu = bank.cpu()
+    for i, it in enumerate(items):
+        assert set(it.keys()) == {"caption", "text_id", "text_embedding", "related_embeddings"}
+        assert it["text_id"] == i and it["text_embedding"].device.type == "cpu"
+        assert torch.equal(it["text_embedding"], torch.from_numpy(x[i:i + 1]))
+        rel = it["related_embeddings"]
+        assert rel.device.type == "cpu" and rel.dtype == torch.float32 and tuple(rel.shape) == (case["k"], helpers.D)
+        assert rel.untyped_storage().nbytes() == case["k"] * helpers.D * 4   # own storage, not a batch view
+        mine = (rel @ xn.T).argmax(dim=1).numpy()
+        theirs = g["related_index"][i]
+        score = (xn[i:i + 1] @ rel.T)[0].numpy()
+        # best first, and every slot within the near-tie tolerance of the reference's choice
+        assert (np.diff(score) <= 1e-3).all()
+        np.testing.assert_allclose(score, g["related_score"][i], atol=1e-3)
+        for slot in range(case["k"]):
+            if mine[slot] == theirs[slot]:
+                # same index => the stored row is bit-identical to the caller's fp32 bank row
+                assert torch.equal(rel[slot], bank_cpu[mine[slot]])
+                np.testing.assert_allclose(rel[slot].double().sum().item(), g["related_rowsum"][i][slot], atol=1e-5)
+            else:
+                assert abs(exact[i, mine[slot]] - exact[i, theirs[slot]]) < 1e-3, (i, slot)
+    if name == "generator_gauss":
+        same = np.mean([(items[i]["related_embeddings"] @ xn.T).argmax(dim=1).numpy().tolist()
+                        == g["related_index"][i].tolist() for i in range(case["n"])])
+        assert same == 1.0                                       # no near-ties in iid Gaussian data
+
+
+def test_append_mode_and_cli(tmp_path):
+    single, multi = _modules()
+    case = recipes.CASES["generator_k1"]
+    _, recs = helpers.case_records(case)
+    paths = helpers.write_case_files(case, recs, tmp_path)
+    out = str(tmp_path / "cli_related.pkl")
+    single.main(["--input_path", paths[0], "--output_path", out, "--topnumber", "2"])
+    first = os.path.getsize(out)
+    items = helpers.read_related_stream(out)
+    assert len(items) == case["n"] and tuple(items[0]["related_embeddings"].shape) == (2, helpers.D)
+    # the reference opens the output with 'ab' (:32): a second run appends, it does not truncate
+    multi.main(["--input_path", paths[0], paths[0], "--output_path", out])       # default topnumber 5
+    assert os.path.getsize(out) > first
+    items = helpers.read_related_stream(out)
+    assert len(items) == 3 * case["n"] and tuple(items[-1]["related_embeddings"].shape) == (5, helpers.D)
+
+
+def test_process_data_batches_and_exclude_self(tmp_path, monkeypatch):
+    from zsaac_b200 import related_pipeline
+    monkeypatch.setattr(related_pipeline, "QUERY_BATCH", 7)      # force several fused launches
+    single, _ = _modules()
+    case = recipes.CASES["generator_gauss"]
+    x, recs = helpers.case_records(case)
+    paths = helpers.write_case_files(case, recs, tmp_path)
+    bank, all_data = single.load_data(paths[0])
+    out = list(single.process_data(bank, all_data, 4, exclude_self=True))
+    xn = torch.nn.functional.normalize(torch.from_numpy(x), dim=-1)
+    _, want = oracle.cosine_topk(xn, xn, 4, self_index=torch.arange(case["n"]))
+    for i, it in enumerate(out):
+        got = (it["related_embeddings"] @ xn.T).argmax(dim=1)
+        assert got.tolist() == want[i].tolist() and i not in got.tolist()
+
+
+def test_val_records_fail_like_the_reference(tmp_path):
+    single, _ = _modules()
+    p = str(tmp_path / "val.pkl")
+    with open(p, "wb") as f:       # embeddings_generator.py:72 writes text_embedding: 0 for val/test
+        pickle.dump([{"audio_embedding": torch.zeros(1, 1024), "caption": "x", "text_embedding": 0}], f)
+    with pytest.raises(AttributeError):
+        single.load_data(p)
+
+
+@pytest.mark.parametrize("name", list(recipes.SEC_CASES))
+def test_sound_effect_choice_matches_reference_golden(name):
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.utils import sound_effect_choice
+    case = recipes.SEC_CASES[name]
+    prefix, bank = recipes.make_sec_inputs(case)
+    g = helpers.golden(name)
+    for dev in ("cpu", "cuda"):
+        idx = sound_effect_choice(torch.from_numpy(prefix).to(dev), torch.from_numpy(bank).to(dev), case["k"])
+        assert idx.dtype == torch.int64 and idx.device.type == "cpu"
+        assert tuple(idx.shape) == (case["q"], case["k"])
+        sim = torch.from_numpy(prefix) @ torch.from_numpy(bank).T
+        for r in range(case["q"]):
+            for slot in range(case["k"]):
+                a, b = int(idx[r, slot]), int(g["index"][r, slot])
+                assert a == b or abs(sim[r, a] - sim[r, b]) < 1e-3
+    # leading batch dims are kept: [2, 2, d] -> [2, 2, k]
+    p3 = torch.from_numpy(np.tile(prefix[:1], (4, 1))).reshape(2, 2, -1)
+    assert tuple(sound_effect_choice(p3, torch.from_numpy(bank), 2).shape) == (2, 2, 2)
+
+
+def test_zero_shot_top1_special_case():
+    import zsaac_b200
+    audio = torch.nn.functional.normalize(helpers.seeded((50, 1024), 5), dim=-1)
+    text = torch.nn.functional.normalize(helpers.seeded((10, 1024), 6), dim=-1)
+    _, idx = zsaac_b200.related_topk(audio.cuda(), text.cuda(), 1, normalize=False)
+    want = oracle.zero_shot_predict(audio, text)
+    sim = audio @ text.T
+    got = idx[:, 0].cpu()
+    assert ((got == want) | ((sim.gather(1, got[:, None]) - sim.gather(1, want[:, None])).abs()[:, 0] < 1e-3)).all()

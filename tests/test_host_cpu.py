@@ -1,0 +1,113 @@
+"""CPU: the host side without a GPU — the C-ABI library loads and exports every declared symbol,
+the product never touches the oracle, and the product path fails loudly without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "zero-shot-aac_b200")
+HEADER = os.path.join(ROOT, "include", "zsaac.h")
+
+import zsaac_b200  # noqa: E402
+from zsaac_b200 import _abi  # noqa: E402
+from zsaac_b200.sharded import shard_bounds  # noqa: E402
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_abi.library_path()), "run `make lib` (or __graft_entry__.build())"
+    assert os.path.realpath(_abi.library_path()).startswith(os.path.realpath(PKG))
+
+
+def test_library_exports_every_header_symbol_and_binding_matches_header():
+    lib = ctypes.CDLL(_abi.library_path())
+    names = declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/zsaac.h but not exported"
+    assert sorted(_abi.SIGNATURES) == names, "ctypes SIGNATURES out of sync with include/zsaac.h"
+
+
+def test_binding_argument_counts_match_header():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, argtypes) in _abi.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^)]*)\)", text)
+        args = m.group(1).strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(argtypes), name
+
+
+def test_no_compute_free_calls_work_without_gpu():
+    lib = _abi.load_library()
+    assert lib.zs_abi_version() == 1
+    assert lib.zs_kernel_name() == b"zs_simtopk_kernel"
+    assert lib.zs_bank_rows(None) == 0 and lib.zs_launch_count(None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda(tmp_path):
+    lib = _abi.load_library()
+    handle = ctypes.c_void_p()
+    assert lib.zs_create(ctypes.byref(handle), 0) == _abi.ZS_ERR_NO_DEVICE
+    assert b"no CPU path" in lib.zs_last_error()
+    q, b = torch.randn(2, 1024), torch.randn(10, 1024)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        zsaac_b200.related_topk(q, b, 3)
+    from zsaac_b200.utils import sound_effect_choice
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sound_effect_choice(q, b, 3)
+    from zsaac_b200.data_handing import embeddings_related_generator as gen
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gen.load_data(str(tmp_path / "missing.pkl"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        next(gen.process_data(b, [{"text_embedding": q[:1]}], 3))
+
+
+def test_missing_library_is_an_error_not_a_fallback(tmp_path):
+    code = ("import os,sys; sys.path.insert(0, %r); os.environ['ZSAAC_B200_LIB']=%r\n"
+            "import zsaac_b200\n"
+            "try:\n    zsaac_b200.load_library()\nexcept OSError as e:\n    print('OSERROR', 'no CPU fallback' in str(e))\n"
+            % (ROOT, str(tmp_path / "nope.so")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "OSERROR True" in out.stdout, out.stdout + out.stderr
+
+
+def test_product_never_imports_the_oracle():
+    offenders = []
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "oracle/" in text:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+
+
+def test_cli_surface_matches_reference():
+    from zsaac_b200.data_handing import embeddings_related_generator as g1
+    from zsaac_b200.data_handing import embeddings_related_generator_wavcaps as g2
+    for mod in (g1, g2):
+        for fn in ("load_data", "process_data", "save_data_to_hdf5", "main"):
+            assert callable(getattr(mod, fn))
+    with pytest.raises(TypeError):
+        g2.load_data("a_single_string.pkl")
+
+
+def test_shard_bounds_cover_the_bank_exactly():
+    for n, w in [(10_000_000, 8), (400_000, 8), (19_195, 4), (49_838, 2), (7, 8), (8, 8), (1, 1)]:
+        b = shard_bounds(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        per = -(-n // w)
+        assert all(hi - lo <= per for lo, hi in b)
+    assert shard_bounds(10_000_000, 8)[3] == (3_750_000, 5_000_000)

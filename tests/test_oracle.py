@@ -1,0 +1,133 @@
+"""CPU: the oracle (oracle/oracle.py) against the golden vectors produced by the reference's own
+functions (tests/golden/make_golden.py), plus its internal consistency."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import recipes
+from oracle import oracle
+
+
+@pytest.mark.parametrize("name", list(recipes.CASES))
+def test_literal_loop_matches_reference_golden(name):
+    case = recipes.CASES[name]
+    x, recs = helpers.case_records(case)
+    g = helpers.golden(name)
+    bank = oracle.build_bank(recs)
+    # bank rows: same values as the reference's (its order is a permutation, stored in the fixture)
+    np.testing.assert_allclose(bank.double().sum(dim=1).numpy()[g["bank_order"]], g["bank_rowsum"],
+                               rtol=0, atol=1e-5)
+    out = list(oracle.process_data_literal(bank, recs, case["k"]))
+    assert len(out) == case["n"]
+    xn = torch.nn.functional.normalize(torch.from_numpy(x), dim=-1)
+    exact = oracle.exact_scores(torch.from_numpy(x), torch.from_numpy(x))
+    for i, item in enumerate(out):
+        rel = item["related_embeddings"]
+        assert rel.shape == (case["k"], helpers.D) and rel.dtype == torch.float32
+        score = (xn[i:i + 1] @ rel.T)[0].numpy()
+        # same scores as the reference picked ...
+        np.testing.assert_allclose(score, g["related_score"][i], atol=2e-6)
+        # ... and the same rows, except where two candidates are tied to within fp32 rounding
+        # (clustered case, duplicate rows): then either row is a correct answer
+        mine = (rel @ xn.T).argmax(dim=1).numpy()
+        theirs = g["related_index"][i]
+        for slot in range(case["k"]):
+            if mine[slot] != theirs[slot]:
+                assert abs(exact[i, mine[slot]] - exact[i, theirs[slot]]) < 5e-6, (i, slot)
+            else:
+                np.testing.assert_allclose(rel[slot].double().sum().item(),
+                                           g["related_rowsum"][i][slot], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", list(recipes.CASES))
+def test_batched_oracle_matches_reference_golden(name):
+    case = recipes.CASES[name]
+    x, recs = helpers.case_records(case)
+    g = helpers.golden(name)
+    q = torch.from_numpy(x)
+    s, idx = oracle.cosine_topk(q, q, case["k"])
+    np.testing.assert_allclose(s.numpy(), g["related_score"], atol=2e-6)
+    exact = oracle.exact_scores(q, q)
+    for i in range(case["n"]):
+        for slot in range(case["k"]):
+            a, b = int(idx[i, slot]), int(g["related_index"][i][slot])
+            # identical / fp32-tied rows: the index choice among them is arbitrary in torch.topk
+            assert a == b or abs(exact[i, a] - exact[i, b]) < 5e-6, (i, slot, a, b)
+    rep = oracle.check_topk(s, idx, q, q, case["k"])
+    assert rep["ok"], rep
+
+
+def test_reference_never_excludes_self():
+    # SURVEY §3A [probe]: slot 0 of related_embeddings is the item itself (score 1.0)
+    g = helpers.golden("generator_gauss")
+    assert (g["related_index"][:, 0] == np.arange(g["related_index"].shape[0])).all()
+    np.testing.assert_allclose(g["related_score"][:, 0], 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(recipes.SEC_CASES))
+def test_sound_effect_choice_matches_reference_golden(name):
+    case = recipes.SEC_CASES[name]
+    prefix, bank = recipes.make_sec_inputs(case)
+    g = helpers.golden(name)
+    idx = oracle.sound_effect_choice(torch.from_numpy(prefix), torch.from_numpy(bank), case["k"])
+    assert idx.dtype == torch.int64
+    assert idx.tolist() == g["index"].tolist()
+    # softmax is monotone: same as the top-k of the raw similarity
+    s, i2 = oracle.cosine_topk(torch.from_numpy(prefix), torch.from_numpy(bank), case["k"], normalize=False)
+    assert i2.tolist() == g["index"].tolist()
+    np.testing.assert_allclose(s.numpy(), g["score"], atol=1e-6)
+
+
+def test_stable_topk_tie_order_and_self_exclusion():
+    bank = torch.eye(8, 64)
+    bank[5] = bank[2]                                   # exact duplicate rows
+    q = bank[2:3].clone()
+    s, i = oracle.cosine_topk(q, bank, 3)
+    assert i[0, :2].tolist() == [2, 5] and s[0, 0] == s[0, 1] == 1.0
+    s, i = oracle.cosine_topk(q, bank, 2, self_index=torch.tensor([2]))
+    assert i[0, 0].item() == 5 and 2 not in i[0].tolist()
+
+
+def test_zero_norm_rows_follow_f_normalize_eps():
+    x = torch.zeros(2, 64)
+    x[1, 0] = 3.0
+    n = oracle.normalize_rows(x)
+    assert torch.equal(n[0], torch.zeros(64)) and n[1, 0] == 1.0
+
+
+def test_merge_lists_equals_global_topk():
+    q = helpers.seeded((17, 64), 5)
+    b = helpers.seeded((1000, 64), 6)
+    k = 7
+    gs, gi = oracle.cosine_topk(q, b, k)
+    parts_s, parts_i = [], []
+    for lo, hi in oracle.shard_bounds(1000, 3):
+        s, i = oracle.cosine_topk(q, b[lo:hi], k)
+        parts_s.append(s)
+        parts_i.append(i + lo)
+    ms, mi = oracle.merge_lists(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, gi)
+    # merging never changes a score's bits
+    assert torch.equal(ms, torch.stack(parts_s).permute(1, 0, 2).reshape(17, -1).gather(
+        1, torch.stack(parts_i).permute(1, 0, 2).reshape(17, -1).argsort(1).gather(
+            1, torch.searchsorted(torch.stack(parts_i).permute(1, 0, 2).reshape(17, -1).sort(1).values, mi))))
+
+
+def test_noise_injection_cosine_to_source():
+    # variance 0.001 at d=1024 gives cos(query, own row) ~ 0.70
+    x = torch.nn.functional.normalize(helpers.seeded((64, 1024), 9), dim=-1)
+    y = oracle.noise_injection(x, 0.001, generator=torch.Generator().manual_seed(3))
+    cos = (x * y).sum(dim=1)
+    assert 0.6 < cos.mean().item() < 0.8
+
+
+def test_check_topk_flags_wrong_answers():
+    q = helpers.seeded((4, 64), 1)
+    b = helpers.seeded((50, 64), 2)
+    s, i = oracle.cosine_topk(q, b, 5)
+    assert oracle.check_topk(s, i, q, b, 5)["ok"]
+    bad_i = i.clone()
+    bad_i[0, 0] = (i[0, 0] + 1) % 50 if ((i[0, 0] + 1) % 50) not in i[0].tolist() else (i[0, 0] + 7) % 50
+    assert not oracle.check_topk(s, bad_i, q, b, 5)["ok"]
+    assert not oracle.check_topk(s + 0.01, i, q, b, 5)["ok"]

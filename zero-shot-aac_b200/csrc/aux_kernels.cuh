@@ -100,7 +100,7 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
-                   int64_t list_stride, int64_t Q, int k, long long idx_offset,
+                   int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
                    float* __restrict__ out_scores, long long* __restrict__ out_idx) {
   const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,9 +117,8 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
     hs[l] = -CUDART_INF_F;
     hi[l] = SENT;
     if (list < S) {
-      const int64_t o = static_cast<int64_t>(list) * list_stride + q * k;
-      hs[l] = scores[o];
-      hi[l] = widen_index(idx[o]);
+      hs[l] = scores[static_cast<int64_t>(list) * score_stride + q * k];
+      hi[l] = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k]);
     } else {
       head[l] = k;  // exhausted
     }
@@ -152,9 +151,9 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
       if (best.src == lane * MERGE_MAX_LISTS_PER_LANE + l) {
         ++head[l];
         if (head[l] < k) {
-          const int64_t o = static_cast<int64_t>(lane + 32 * l) * list_stride + q * k + head[l];
-          hs[l] = scores[o];
-          hi[l] = widen_index(idx[o]);
+          const int64_t list = lane + 32 * l;
+          hs[l] = scores[list * score_stride + q * k + head[l]];
+          hi[l] = widen_index(idx[list * index_stride + q * k + head[l]]);
         }
       }
     }

@@ -62,13 +62,13 @@ struct DeviceGuard {
 struct zs_ctx {
   int device = 0;
   int sm_count = 0;
-  int cta_group = 1;           // 1, or 2 (CTA pairs, cta_group::2); env ZSAAC_CTA_GROUP overrides
+  int cta_group_override = 0;  // 0 = choose per search; env ZSAAC_CTA_GROUP=1|2 pins it (tests)
   EncodeTiledFn encode = nullptr;
 
   __nv_bfloat16* bank = nullptr;
   int64_t bank_rows = 0;
   int bank_d = 0;
-  CUtensorMap bank_map;        // box {64, 256 / cta_group}
+  CUtensorMap bank_map[2];     // [0]: box {64, 256} (cta_group::1)  [1]: box {64, 128} (cta_group::2)
 
   __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
   int64_t q_ws_rows = 0;
@@ -78,6 +78,10 @@ struct zs_ctx {
   int* err_flag = nullptr;
 
   int64_t launches = 0;
+
+  bool profiling = false;          // zs_profile_enable
+  cudaEvent_t* prof_ev = nullptr;  // 2 * ZS_PROFILE_RING events (start, stop)
+  int prof_count = 0;              // launches recorded since enable (ring wraps)
 };
 
 namespace {
@@ -101,14 +105,23 @@ int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t row
 int kcap_for(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
 
 struct Plan {
-  int m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
+  int cg, m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
 };
+
+// CTA pairs (cta_group::2, 256-row query tiles, half the shared-memory traffic per MMA) pay off
+// once there are several query tiles; a single 128-row tile streams the bank fastest from
+// independent CTAs.
+int pick_cta_group(const zs_ctx* ctx, int64_t Q) {
+  if (ctx->cta_group_override) return ctx->cta_group_override;
+  return Q > 256 ? 2 : 1;
+}
 
 // Split the bank into `chunks` contiguous runs of 256-row tiles so that (query tiles x chunks)
 // work units fill the SMs in whole waves with the least padded work.
 Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
   Plan pl{};
-  const int cg = ctx->cta_group;
+  const int cg = pick_cta_group(ctx, Q);
+  pl.cg = cg;
   const int workers = std::max(1, ctx->sm_count / cg);
   pl.m_tiles = static_cast<int>((Q + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
   pl.n_tiles = static_cast<int>((ctx->bank_rows + zs::BLOCK_N - 1) / zs::BLOCK_N);
@@ -181,7 +194,14 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  ZS_CUDA(cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map, p));
+  const bool prof = ctx->profiling && !DUMP;
+  const int slot = ctx->prof_count % ZS_PROFILE_RING;
+  if (prof) ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot], st));
+  ZS_CUDA(cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p));
+  if (prof) {
+    ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot + 1], st));
+    ctx->prof_count += 1;
+  }
   ctx->launches += 1;
   return ZS_OK;
 }
@@ -246,7 +266,7 @@ int zs_create(zs_ctx** out, int device) {
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   const char* cg = getenv("ZSAAC_CTA_GROUP");
-  if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group = cg[0] - '0';
+  if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group_override = cg[0] - '0';
   e = cudaMalloc(&ctx->err_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->err_flag, 0, sizeof(int));
   if (e != cudaSuccess) {
@@ -265,6 +285,10 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->part_scores);
   cudaFree(ctx->part_idx);
   cudaFree(ctx->err_flag);
+  if (ctx->prof_ev) {
+    for (int i = 0; i < 2 * ZS_PROFILE_RING; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+    delete[] ctx->prof_ev;
+  }
   delete ctx;
   return ZS_OK;
 }
@@ -293,7 +317,9 @@ int zs_bank_alloc(zs_ctx* ctx, int64_t n_rows, int d) {
     ctx->bank_rows = n_rows;
     ctx->bank_d = d;
   }
-  return encode_rows_map(ctx, &ctx->bank_map, ctx->bank, n_rows, d, zs::BLOCK_N / ctx->cta_group);
+  int rc = encode_rows_map(ctx, &ctx->bank_map[0], ctx->bank, n_rows, d, zs::BLOCK_N);
+  if (rc) return rc;
+  return encode_rows_map(ctx, &ctx->bank_map[1], ctx->bank, n_rows, d, zs::BLOCK_N / 2);
 }
 
 int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_row, int in_dtype,
@@ -338,6 +364,37 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 
 int64_t zs_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int zs_profile_enable(zs_ctx* ctx, int enable) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_profile_enable: ctx is null");
+  DeviceGuard guard(ctx->device);
+  if (enable && !ctx->prof_ev) {
+    ctx->prof_ev = new (std::nothrow) cudaEvent_t[2 * ZS_PROFILE_RING];
+    if (!ctx->prof_ev) return fail(ZS_ERR_INVALID, "zs_profile_enable: out of host memory");
+    for (int i = 0; i < 2 * ZS_PROFILE_RING; ++i) ZS_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+  }
+  ctx->profiling = enable != 0;
+  ctx->prof_count = 0;
+  return ZS_OK;
+}
+
+int zs_profile_read(zs_ctx* ctx, float* ms_out, int max_entries, int* n_entries) {
+  if (!ctx || !ms_out || !n_entries || max_entries < 0)
+    return fail(ZS_ERR_INVALID, "zs_profile_read: bad argument");
+  *n_entries = 0;
+  if (!ctx->prof_ev) return ZS_OK;
+  DeviceGuard guard(ctx->device);
+  const int have = std::min(ctx->prof_count, (int)ZS_PROFILE_RING);
+  const int n = std::min(have, max_entries);
+  const int first = ctx->prof_count - have;   // oldest launch still in the ring
+  for (int j = 0; j < n; ++j) {
+    const int slot = (first + j) % ZS_PROFILE_RING;
+    ZS_CUDA(cudaEventSynchronize(ctx->prof_ev[2 * slot + 1]));
+    ZS_CUDA(cudaEventElapsedTime(&ms_out[j], ctx->prof_ev[2 * slot], ctx->prof_ev[2 * slot + 1]));
+  }
+  *n_entries = n;
+  return ZS_OK;
+}
+
 int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, int normalize_queries,
               const int64_t* self_index, int64_t index_offset, float* out_scores,
               int64_t* out_indices, void* stream) {
@@ -378,27 +435,28 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   p.part_idx = ctx->part_idx;
   p.dump = nullptr;
   p.err_flag = ctx->err_flag;
-  rc = (ctx->cta_group == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
-                             : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
+                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
   if (rc) return rc;
 
   const int64_t blocks = (Q * 32 + 255) / 256;
   zs::merge_lists_kernel<int><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      ctx->part_scores, ctx->part_idx, pl.chunks, Q * k, Q, k, index_offset, out_scores,
+      ctx->part_scores, ctx->part_idx, pl.chunks, Q * k, Q * k, Q, k, index_offset, out_scores,
       reinterpret_cast<long long*>(out_indices));
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
 }
 
-int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t list_stride,
-             int64_t Q, int k, float* out_scores, int64_t* out_indices, void* stream) {
+int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, int64_t score_stride,
+             int64_t index_stride, int64_t Q, int k, float* out_scores, int64_t* out_indices,
+             void* stream) {
   if (!ctx) return fail(ZS_ERR_INVALID, "zs_merge: ctx is null");
   if (S < 1 || S > zs::MERGE_MAX_LISTS)
     return fail(ZS_ERR_INVALID, "zs_merge: S=%d outside [1, %d]", S, zs::MERGE_MAX_LISTS);
-  if (k < 1 || Q < 0 || list_stride < Q * k)
-    return fail(ZS_ERR_INVALID, "zs_merge: Q=%lld k=%d list_stride=%lld", (long long)Q, k,
-                (long long)list_stride);
+  if (k < 1 || Q < 0 || score_stride < Q * k || index_stride < Q * k)
+    return fail(ZS_ERR_INVALID, "zs_merge: Q=%lld k=%d score_stride=%lld index_stride=%lld",
+                (long long)Q, k, (long long)score_stride, (long long)index_stride);
   if (Q == 0) return ZS_OK;
   if (!scores || !indices || !out_scores || !out_indices)
     return fail(ZS_ERR_INVALID, "zs_merge: null pointer");
@@ -406,7 +464,8 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (Q * 32 + 255) / 256;
   zs::merge_lists_kernel<long long><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      scores, reinterpret_cast<const long long*>(indices), S, list_stride, Q, k, 0ll, out_scores,
+      scores, reinterpret_cast<const long long*>(indices), S, score_stride, index_stride, Q, k, 0ll,
+      out_scores,
       reinterpret_cast<long long*>(out_indices));
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
@@ -472,8 +531,8 @@ int zs_debug_scores(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, in
   p.k = 1;
   p.dump = out_scores;
   p.err_flag = ctx->err_flag;
-  return (ctx->cta_group == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, true, st)
-                               : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, true, st);
+  return (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, true, st)
+                      : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, true, st);
 }
 
 }  // extern "C"

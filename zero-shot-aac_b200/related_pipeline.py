@@ -1,0 +1,130 @@
+"""Shared implementation of the related-caption generator scripts.
+
+The reference has two near-identical scripts (data_handing/embeddings_related_generator.py and
+embeddings_related_generator_wavcaps.py); they differ only in load_data taking one path or a
+list.  Both module mirrors in data_handing/ delegate here.
+
+What changes against the reference: the N-iteration Python loop of process_data
+(embeddings_related_generator.py:19-28 — per item: CPU normalise, H2D, cosine_similarity over the
+whole bank, topk, gather, two D2H syncs) becomes batches of queries through one fused
+similarity+top-k launch.  What does not change: function names, arguments, lazy generator
+semantics, the mutated item dicts and the append-mode stream of per-record pickles.
+"""
+from __future__ import annotations
+
+import pickle
+from typing import Iterable, Iterator, List, Sequence, Tuple, Union
+
+import torch
+
+from .retrieval import RelatedBank, _require_cuda, bank_for
+
+try:  # the reference wraps the writer loop in tqdm (embeddings_related_generator.py:33)
+    from tqdm import tqdm
+except Exception:  # pragma: no cover - tqdm is present in the image
+    def tqdm(it, total=None):
+        return it
+
+# queries per fused launch; 16384 x k=5 gathered rows = 335 MB of pinned staging at d=1024
+QUERY_BATCH = 16384
+
+
+def _read_records(paths: Sequence[str]) -> List[dict]:
+    all_data: List[dict] = list()
+    for path in paths:
+        with open(path, "rb") as f:
+            all_data = all_data + pickle.load(f)        # reference :11-12 / wavcaps :11-13
+    return all_data
+
+
+def load_data(raw_path: Union[str, Sequence[str]]) -> Tuple[torch.Tensor, List[dict]]:
+    """(bank, all_data): bank = fp32 [N, d] unit rows on the GPU, all_data = the pickled records.
+
+    Reference: embeddings_related_generator.py:9-17 (raw_path: str) and
+    embeddings_related_generator_wavcaps.py:9-18 (raw_path: list of str).  The reference routes
+    the rows through `set()` (:15), which keeps value-duplicates (tensors hash by identity) and
+    scrambles the order; here the bank keeps input order, which only affects how exact ties are
+    ordered.  Val/test records carry `text_embedding: 0` (embeddings_generator.py:72) and fail
+    here exactly as they do in the reference (int has no .cpu()).
+    """
+    _require_cuda()
+    paths = [raw_path] if isinstance(raw_path, (str, bytes)) else list(raw_path)
+    all_data = _read_records(paths)
+    all_captions = [raw_data["text_embedding"].cpu() for raw_data in all_data]      # :14
+    host = torch.cat(all_captions, dim=0).to(torch.float32).contiguous().pin_memory()
+    dev = host.to("cuda", non_blocking=True)                                        # :15
+    # F.normalize(..., dim=-1) (:17) through the native library; the bf16 search copy is built
+    # from the same tensor lazily by process_data
+    rb = RelatedBank(dev.shape[0], dev.shape[1], device=dev.device)
+    bank = rb.normalize_rows(dev)
+    rb.upload(bank, 0, normalize=True)
+    _register_bank(bank, rb)
+    return bank, all_data
+
+
+def _register_bank(bank: torch.Tensor, rb: RelatedBank) -> None:
+    """Let process_data find the bf16 copy load_data already built for this tensor."""
+    import weakref
+    from . import retrieval
+    key = (bank.data_ptr(), tuple(bank.shape), bank.dtype, str(bank.device), bank._version, True)
+    if len(retrieval._BANK_CACHE) >= retrieval._BANK_CACHE_MAX:
+        retrieval._BANK_CACHE.pop(next(iter(retrieval._BANK_CACHE)))[1].close()
+    retrieval._BANK_CACHE[key] = (weakref.ref(bank), rb)
+
+
+def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnumber: int,
+                 *, exclude_self: bool = False) -> Iterator[dict]:
+    """Yield every item with `related_embeddings` = its top-`topnumber` bank rows, best first.
+
+    Reference: embeddings_related_generator.py:19-28.  valid_text_embs is the fp32 bank returned
+    by load_data (CUDA).  For each item the query is F.normalize(item['text_embedding']) (:21),
+    ranked by cosine similarity against the bank (:22); the k rows are gathered from
+    valid_text_embs itself (:23), so they are bit-identical to the reference's whenever the chosen
+    index is.  item['text_embedding'] is moved to the CPU (:25).  Like the reference there is no
+    self-exclusion unless exclude_self=True (opt-in; assumes item i is bank row i).
+    """
+    _require_cuda()
+    if not valid_text_embs.is_cuda:
+        raise ValueError("valid_text_embs must be the CUDA bank returned by load_data "
+                         "(no CPU path exists)")
+    topnumber = int(topnumber)
+    rb = bank_for(valid_text_embs, normalize=True)
+    device = valid_text_embs.device
+    d = valid_text_embs.shape[1]
+    batch: List[dict] = []
+    base = 0
+
+    def flush(items: List[dict], first: int) -> Iterator[dict]:
+        q_host = torch.cat([it["text_embedding"].detach().cpu().reshape(1, -1) for it in items],
+                           dim=0).to(torch.float32).pin_memory()
+        q_dev = q_host.to(device, non_blocking=True)
+        self_index = None
+        if exclude_self:
+            self_index = torch.arange(first, first + len(items), dtype=torch.int64, device=device)
+        _, ids = rb.search(q_dev, topnumber, normalize_queries=True, self_index=self_index)
+        related = rb.gather_rows(valid_text_embs, ids)                 # [B, k, d] fp32 on the GPU
+        related_host = torch.empty(related.shape, dtype=torch.float32).pin_memory()
+        related_host.copy_(related, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        for j, item in enumerate(items):
+            item["text_embedding"] = item["text_embedding"].cpu()      # :25
+            # own storage per record: a view would pickle the whole batch buffer with each item
+            item["related_embeddings"] = related_host[j].clone()       # :26  [k, d] fp32 CPU
+            yield item
+
+    for item in all_data:
+        batch.append(item)
+        if len(batch) == QUERY_BATCH:
+            yield from flush(batch, base)
+            base += len(batch)
+            batch = []
+    if batch:
+        yield from flush(batch, base)
+
+
+def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, total_items: int) -> None:
+    """Append one pickle per record to output_path (reference :30-34; the name is historical —
+    the format is a pickle stream, read back by dataset/dataset.py:64-78)."""
+    with open(output_path, "ab") as file:
+        for i, item in enumerate(tqdm(processed_data_gen, total=total_items)):
+            pickle.dump(item, file)

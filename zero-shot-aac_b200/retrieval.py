@@ -150,17 +150,30 @@ class RelatedBank:
 
     # ------------------------------------------------------------------ helpers on the same ctx
     def merge(self, scores: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """k-way merge of [S, Q, k] sorted lists -> [Q, k] under (score desc, index asc)."""
+        """k-way merge of [S, Q, k] sorted lists -> [Q, k] under (score desc, index asc).
+
+        The S lists may be strided views (dim 0 stride arbitrary, [Q, k] blocks contiguous), e.g.
+        slices of one all-gathered byte buffer."""
         if scores.dim() != 3 or scores.shape != indices.shape:
             raise ValueError("merge expects scores and indices of identical shape [S, Q, k]")
         s, q, k = scores.shape
-        scores = scores.to(torch.float32).contiguous()
-        indices = indices.to(torch.int64).contiguous()
+        if scores.dtype != torch.float32 or indices.dtype != torch.int64:
+            raise TypeError("merge expects float32 scores and int64 indices")
+
+        def blocks_contiguous(t):
+            return s == 0 or q == 0 or (t.stride(2) == 1 and t.stride(1) == k)
+
+        if not blocks_contiguous(scores):
+            scores = scores.contiguous()
+        if not blocks_contiguous(indices):
+            indices = indices.contiguous()
         out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
         out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        s_stride = scores.stride(0) if s > 1 else q * k
+        i_stride = indices.stride(0) if s > 1 else q * k
         with torch.cuda.device(self.device):
             _abi.check(self._lib.zs_merge(
-                self._ctx, scores.data_ptr(), indices.data_ptr(), s, q * k, q, k,
+                self._ctx, scores.data_ptr(), indices.data_ptr(), s, s_stride, i_stride, q, k,
                 out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(self.device)))
         return out_s, out_i
 
@@ -195,6 +208,17 @@ class RelatedBank:
         _abi.check(self._lib.zs_plan(self._ctx, int(n_queries), int(k), ctypes.byref(a),
                                      ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
+
+    def profile(self, enable: bool) -> None:
+        """Bracket every fused-kernel launch with CUDA events (ring of 256 launches)."""
+        _abi.check(self._lib.zs_profile_enable(self._ctx, 1 if enable else 0))
+
+    def kernel_times_ms(self) -> list:
+        """Device durations of the fused kernel launches recorded since profile(True)."""
+        buf = (ctypes.c_float * 256)()
+        n = ctypes.c_int()
+        _abi.check(self._lib.zs_profile_read(self._ctx, buf, 256, ctypes.byref(n)))
+        return [float(buf[j]) for j in range(n.value)]
 
     @property
     def launch_count(self) -> int:
