@@ -11,12 +11,13 @@
 //   * warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128*CG, N=256, K=16) into one of
 //                two 256-column TMEM accumulators
 //   * warp 2   : TMEM allocator
-//   * warps 4-7: epilogue      — thread t owns query row t of the tile (TMEM lane t), reads its
-//                256 scores with tcgen05.ld and maintains a sorted top-k list in registers; the
+//   * warps 4-11: epilogue     — two warps per TMEM lane quarter; thread t of warp w owns query row
+//                32*(w%4)+t and the 128-column half (w-4)/4 of every bank tile: it reads its
+//                scores with tcgen05.ld and maintains a sorted top-k list in registers; the
 //                epilogue of bank tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
 // A work unit is (query tile, bank chunk); units are walked persistently with a static stride.
-// Every unit writes its k best (score, column) pairs per row; merge_lists_kernel reduces the
-// chunks.  CG == 2 pairs two CTAs of a cluster on a 256-row query tile (cta_group::2): each CTA
+// Every unit writes, per row and column half, its k best (score, column) pairs;
+// merge_lists_kernel reduces the 2 x chunks lists.  CG == 2 pairs two CTAs of a cluster on a 256-row query tile (cta_group::2): each CTA
 // loads its own 128 query rows and half of the bank tile.
 #pragma once
 
@@ -33,9 +34,11 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512: the whole tensor memory of the SM
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_EPI_WARPS = 8;                 // 2 per TMEM lane quarter (column halves)
+constexpr int EPI_HALVES = NUM_EPI_WARPS / 4;
+constexpr int EPI_COLS = BLOCK_N / EPI_HALVES;   // columns of a tile each epilogue thread scans
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);  // 384
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 template <int CG>
@@ -62,36 +65,32 @@ struct SimTopkParams {
   int k;                 // requested list length (<= KCAP)
   const long long* self_index;  // nullable [Q]: global bank index to skip
   long long index_offset;       // global index of bank row 0 of this shard
-  float* part_scores;    // [num_chunks, Q, k]
-  int* part_idx;         // [num_chunks, Q, k]  column within the shard
+  float* part_scores;    // [num_chunks * EPI_HALVES, Q, k]
+  int* part_idx;         // [num_chunks * EPI_HALVES, Q, k]  column within the shard
   float* dump;           // DUMP mode: [Q, n_bank]
   int* err_flag;
 };
 
 // Sorted (descending score; equal scores keep arrival order = ascending column) list in registers.
+// The list always has KCAP physical slots; for a requested length k < KCAP the top KCAP-k slots
+// are pinned with +inf so that the live entries are slots [KCAP-k, KCAP) and the admission
+// threshold is always the LAST slot — every register index stays a compile-time constant.
 template <int KCAP>
 struct TopkList {
   float s[KCAP];
   int i[KCAP];
 
-  __device__ __forceinline__ void init() {
+  __device__ __forceinline__ void init(int k) {
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) {
-      s[j] = -CUDART_INF_F;
+      s[j] = (j < KCAP - k) ? CUDART_INF_F : -CUDART_INF_F;
       i[j] = IDX_SENTINEL;
     }
   }
 
-  // value at position k-1 (the admission threshold for a length-k list)
-  __device__ __forceinline__ float kth(int k) const {
-    float t = s[KCAP - 1];
-#pragma unroll
-    for (int j = 0; j < KCAP - 1; ++j)
-      if (j == k - 1) t = s[j];
-    return t;
-  }
+  __device__ __forceinline__ float threshold() const { return s[KCAP - 1]; }
 
-  // Insert (v, idx); precondition v > s[KCAP-1] or the element simply falls off the end.
+  // Insert (v, idx) with v > threshold(): shifts the tail down by one, dropping the last slot.
   __device__ __forceinline__ void insert(float v, int idx) {
     bool gt[KCAP];
 #pragma unroll
@@ -105,6 +104,20 @@ struct TopkList {
     i[0] = gt[0] ? idx : i[0];
   }
 };
+
+// r[j] for a run-time j without local memory: a 5-level select tree (31 SEL).
+__device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) a[t] = (j & 1) ? r[2 * t + 1] : r[2 * t];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) b[t] = (j & 2) ? a[2 * t + 1] : a[2 * t];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) c[t] = (j & 4) ? b[2 * t + 1] : b[2 * t];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) d[t] = (j & 8) ? c[2 * t + 1] : c[2 * t];
+  return (j & 16) ? d[1] : d[0];
+}
 
 template <int KCAP, int CG, bool DUMP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -141,7 +154,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), NUM_EPI_THREADS * CG);
+      ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);   // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -238,6 +251,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue: running top-k
     const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = (warp - EPI_WARP0) >> 2;       // which EPI_COLS-wide slice of every tile
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t tmem_lane = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t tile_count = 0;
@@ -254,8 +268,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const long long c = g - p.index_offset;
         if (g >= 0 && c >= 0 && c < p.n_bank) self_col = static_cast<int>(c);
       }
-      list.init();
-      float thr = -CUDART_INF_F;
+      list.init(p.k);
+      float thr = list.threshold();
       for (int t = t0; t < t1; ++t, ++tile_count) {
         const uint32_t acc = tile_count & 1u;
         const uint32_t acc_phase = (tile_count >> 1) & 1u;
@@ -263,7 +277,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ptx::tc_fence_after();
         const int col_tile = t * BLOCK_N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = half * EPI_COLS; c0 < (half + 1) * EPI_COLS; c0 += 32) {
           uint32_t r[32];
           __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
           ptx::tmem_ld_32x32(tmem_base + tmem_lane + acc * BLOCK_N + c0, r);
@@ -283,36 +297,38 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < 32; ++j)
               if (__uint_as_float(r[j]) > thr) cand |= (1u << j);
             if (cand != 0) {
-              // rare path: spill the 32 scores to local memory so they can be indexed dynamically
-              float tmp[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(r[j]);
+              // per-thread rare path (but some lane of the warp takes it for most chunks)
               while (cand != 0) {
                 const int j = __ffs(cand) - 1;
                 cand &= cand - 1;
-                const float v = tmp[j];
+                const float v = __uint_as_float(select32(r, j));
                 const int col = col0 + j;
                 if (v > thr && col < p.n_bank && col != self_col) {
                   list.insert(v, col);
-                  thr = list.kth(p.k);
+                  thr = list.threshold();
                 }
               }
             }
           }
         }
-        // this thread is done with accumulator `acc`: hand it back to the MMA issuer
+        // this warp is done with accumulator `acc` (tcgen05.wait::ld is warp-collective): hand
+        // it back to the MMA issuer with one arrival per warp
         ptx::tc_fence_before();
-        if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
-        else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+        }
       }
       if constexpr (!DUMP) {
         if (row < p.Q) {
-          const size_t o = (static_cast<size_t>(chunk) * p.Q + row) * p.k;
+          const size_t o = (static_cast<size_t>(chunk * EPI_HALVES + half) * p.Q + row) * p.k;
+          const int pinned = KCAP - p.k;   // slots [pinned, KCAP) are the live entries
 #pragma unroll
           for (int j = 0; j < KCAP; ++j) {
-            if (j < p.k) {
-              p.part_scores[o + j] = list.s[j];
-              p.part_idx[o + j] = list.i[j];
+            if (j >= pinned) {
+              p.part_scores[o + j - pinned] = list.s[j];
+              p.part_idx[o + j - pinned] = list.i[j];
             }
           }
         }

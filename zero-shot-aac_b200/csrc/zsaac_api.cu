@@ -72,7 +72,7 @@ struct zs_ctx {
 
   __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
   int64_t q_ws_rows = 0;
-  float* part_scores = nullptr;   // [chunks, Q, k]
+  float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
   int64_t part_elems = 0;
   int* err_flag = nullptr;
@@ -125,7 +125,7 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
   const int workers = std::max(1, ctx->sm_count / cg);
   pl.m_tiles = static_cast<int>((Q + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
   pl.n_tiles = static_cast<int>((ctx->bank_rows + zs::BLOCK_N - 1) / zs::BLOCK_N);
-  const int max_chunks = std::min(pl.n_tiles, zs::MERGE_MAX_LISTS);
+  const int max_chunks = std::min(pl.n_tiles, zs::MERGE_MAX_LISTS / zs::EPI_HALVES);
   double best_cost = 1e300;
   int best_s = 1;
   for (int s = 1; s <= max_chunks; ++s) {
@@ -152,7 +152,7 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
     ctx->q_ws_rows = Q;
   }
   const Plan pl = make_plan(ctx, Q, k);
-  const int64_t need = static_cast<int64_t>(pl.chunks) * Q * k;
+  const int64_t need = static_cast<int64_t>(pl.chunks) * zs::EPI_HALVES * Q * k;
   if (need > ctx->part_elems) {
     if (ctx->part_scores) { ZS_CUDA(cudaFree(ctx->part_scores)); ctx->part_scores = nullptr; }
     if (ctx->part_idx) { ZS_CUDA(cudaFree(ctx->part_idx)); ctx->part_idx = nullptr; }
@@ -441,7 +441,8 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
 
   const int64_t blocks = (Q * 32 + 255) / 256;
   zs::merge_lists_kernel<int><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      ctx->part_scores, ctx->part_idx, pl.chunks, Q * k, Q * k, Q, k, index_offset, out_scores,
+      ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k, Q, k, index_offset,
+      out_scores,
       reinterpret_cast<long long*>(out_indices));
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
