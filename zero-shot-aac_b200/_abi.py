@@ -51,6 +51,7 @@ SIGNATURES = {
     "zs_profile_enable": (_int, [_c_ctx, _int]),
     "zs_profile_read": (_int, [_c_ctx, ctypes.POINTER(ctypes.c_float), _int, ctypes.POINTER(_int)]),
     "zs_debug_scores": (_int, [_c_ctx, _ptr, _i64, _int, _int, _ptr, _ptr]),
+    "zs_debug_trace": (_int, [_c_ctx, _ptr]),
 }
 
 _lib = None

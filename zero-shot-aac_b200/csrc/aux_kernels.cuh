@@ -18,18 +18,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row.  d is a multiple of 64, so every lane handles whole 8-byte/16-byte vectors.
+// One warp per row.  d is a multiple of 4 (64 on the search path), so every lane handles whole
+// 8-byte/16-byte vectors.
 // The sum of squares is accumulated in a fixed order (lane-strided, then xor butterfly), so the
 // result does not depend on the launch geometry.
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
-                      int d, int normalize) {
+                      int64_t n_rows_out, int d, int normalize) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const InT* src = in + row * d;
+  if (row >= n_rows_out) return;
   OutT* dst = out + row * d;
+  if (row >= n_rows) {
+    // padding rows [n_rows, n_rows_out): zeros, so the consumer's TMA boxes never leave the tensor
+    for (int c = lane * 4; c < d; c += 128) {
+      if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else *reinterpret_cast<uint2*>(dst + c) = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  const InT* src = in + row * d;
   float scale = 1.0f;
   if (normalize) {
     float ss = 0.0f;
@@ -74,14 +83,15 @@ normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Merge: one warp per query; lane l owns lists l, l+32, ... (at most MERGE_MAX_LISTS_PER_LANE).
-constexpr int MERGE_MAX_LISTS_PER_LANE = 8;
+// Merge: one warp per query; lane l owns lists l, l+32, ... (LPL = lists per lane, a template
+// parameter so that the common small merges keep a small register footprint).
+constexpr int MERGE_MAX_LISTS_PER_LANE = 16;
 constexpr int MERGE_MAX_LISTS = 32 * MERGE_MAX_LISTS_PER_LANE;
 
 struct Cand {
   float s;
   long long i;
-  int src;  // lane * MERGE_MAX_LISTS_PER_LANE + slot : makes the order strict even for duplicates
+  int src;  // lane * LPL + slot : makes the order strict even for duplicates
 };
 
 // int32 lists (chunk partials of the fused kernel) mark empty slots with 0x7fffffff
@@ -97,7 +107,7 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
   return a.src < b.src;
 }
 
-template <typename IdxT>
+template <typename IdxT, int LPL>
 __global__ void __launch_bounds__(256)
 merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
                    int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
@@ -107,11 +117,11 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
   if (q >= Q) return;
 
   const long long SENT = 0x7fffffffffffffffll;
-  int head[MERGE_MAX_LISTS_PER_LANE];
-  float hs[MERGE_MAX_LISTS_PER_LANE];
-  long long hi[MERGE_MAX_LISTS_PER_LANE];
+  int head[LPL];
+  float hs[LPL];
+  long long hi[LPL];
 #pragma unroll
-  for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
+  for (int l = 0; l < LPL; ++l) {
     const int list = lane + 32 * l;
     head[l] = 0;
     hs[l] = -CUDART_INF_F;
@@ -127,9 +137,9 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
   for (int r = 0; r < k; ++r) {
     Cand best{-CUDART_INF_F, SENT, 0x7fffffff};
 #pragma unroll
-    for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
+    for (int l = 0; l < LPL; ++l) {
       if (head[l] < k) {
-        const Cand c{hs[l], hi[l], lane * MERGE_MAX_LISTS_PER_LANE + l};
+        const Cand c{hs[l], hi[l], lane * LPL + l};
         if (cand_better(c, best)) best = c;
       }
     }
@@ -147,8 +157,8 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
     }
     // the owner of the winning list advances it
 #pragma unroll
-    for (int l = 0; l < MERGE_MAX_LISTS_PER_LANE; ++l) {
-      if (best.src == lane * MERGE_MAX_LISTS_PER_LANE + l) {
+    for (int l = 0; l < LPL; ++l) {
+      if (best.src == lane * LPL + l) {
         ++head[l];
         if (head[l] < k) {
           const int64_t list = lane + 32 * l;

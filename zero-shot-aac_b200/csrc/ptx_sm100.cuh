@@ -121,6 +121,14 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtenso
       : "memory");
 }
 
+// Pull one box of a tiled tensor into L2 ahead of the load that will consume it.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

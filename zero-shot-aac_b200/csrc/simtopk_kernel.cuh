@@ -31,7 +31,11 @@ constexpr int BLOCK_M = 128;   // query rows per CTA
 constexpr int BLOCK_N = 256;   // bank rows per accumulator tile
 constexpr int BLOCK_K = 64;    // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+// smem ring depth: a slot holds one K-step of operands, 48 KiB for a single CTA (16 KiB queries +
+// 32 KiB bank) and 32 KiB per CTA of a pair (16 + 16), so a pair can run 6 stages deep
+template <int CG>
+constexpr int num_stages() { return CG == 2 ? 6 : 4; }
+constexpr int MAX_STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512: the whole tensor memory of the SM
 constexpr int EPI_WARP0 = 4;
@@ -47,7 +51,7 @@ template <int CG>
 constexpr int stage_bytes() { return A_STAGE_BYTES + b_stage_bytes<CG>(); }
 constexpr int BARRIER_BYTES = 256;
 template <int CG>
-constexpr int smem_bytes() { return STAGES * stage_bytes<1>() + BARRIER_BYTES + 1024; }
+constexpr int smem_bytes() { return num_stages<CG>() * stage_bytes<CG>() + BARRIER_BYTES + 1024; }
 
 constexpr int IDX_SENTINEL = 0x7fffffff;
 
@@ -69,7 +73,16 @@ struct SimTopkParams {
   int* part_idx;         // [num_chunks * EPI_HALVES, Q, k]  column within the shard
   float* dump;           // DUMP mode: [Q, n_bank]
   int* err_flag;
+  unsigned long long* trace;  // nullable: [gridDim.x, 8] globaltimer stamps (zs_debug_trace)
 };
+
+__device__ __forceinline__ void trace_stamp(const SimTopkParams& p, int slot) {
+  if (p.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[static_cast<size_t>(blockIdx.x) * 8 + slot] = t;
+  }
+}
 
 // Sorted (descending score; equal scores keep arrival order = ascending column) list in registers.
 // The list always has KCAP physical slots; for a requested length k < KCAP the top KCAP-k slots
@@ -128,7 +141,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base_u32 - raw_u32);
 
-  constexpr int STAGE_STRIDE = stage_bytes<1>();  // ring slot size (CG == 2 uses 32 of the 48 KiB)
+  constexpr int STAGES = num_stages<CG>();
+  constexpr int STAGE_STRIDE = stage_bytes<CG>();
   constexpr int B_BYTES = b_stage_bytes<CG>();
   constexpr uint32_t TX_BYTES = static_cast<uint32_t>(CG) * (A_STAGE_BYTES + B_BYTES);
 
@@ -146,6 +160,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const bool is_leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {
+    trace_stamp(p, 0);                                   // kernel entry
+    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + 6] = clock64();
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
@@ -163,6 +179,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (threadIdx.x == 0) trace_stamp(p, 1);               // barriers + TMEM ready
 
   // static persistent schedule: all roles walk the same unit list
   const int worker = static_cast<int>(blockIdx.x) / CG;
@@ -174,13 +191,10 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t full_remote[STAGES];
-#pragma unroll
-      for (int s = 0; s < STAGES; ++s) {
-        full_remote[s] = full_bar(s);
-        if constexpr (CG == 2) {
-          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_remote[s]) : "r"(full_bar(s)));
-        }
+      // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
+      uint32_t full_leader0 = full_bar(0);
+      if constexpr (CG == 2) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
       }
       for (int u = worker; u < num_units; u += num_workers) {
         const int m_tile = u % p.num_m_tiles;
@@ -191,6 +205,9 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = t0; t < t1; ++t) {
           const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
+            //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
+            //  only look-ahead)
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
             const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
             const uint32_t b_dst = a_dst + A_STAGE_BYTES;
@@ -200,8 +217,9 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
             } else {
               if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
-              ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_remote[stage], kb * BLOCK_K, q_row);
-              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_remote[stage], kb * BLOCK_K, b_row);
+              const uint32_t full_leader = full_leader0 + 8u * stage;
+              ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
+              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -275,6 +293,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t acc_phase = (tile_count >> 1) & 1u;
         ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, ERR_EPILOGUE);
         ptx::tc_fence_after();
+        if (tile_count == 0 && warp == EPI_WARP0 && lane == 0) trace_stamp(p, 2);  // first tile's MMAs done
         const int col_tile = t * BLOCK_N;
 #pragma unroll 1
         for (int c0 = half * EPI_COLS; c0 < (half + 1) * EPI_COLS; c0 += 32) {
@@ -320,6 +339,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
         }
       }
+      if (warp == EPI_WARP0 && lane == 0) trace_stamp(p, 3);   // last tile of the unit scanned
       if constexpr (!DUMP) {
         if (row < p.Q) {
           const size_t o = (static_cast<size_t>(chunk * EPI_HALVES + half) * p.Q + row) * p.k;
@@ -336,9 +356,14 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   }
 
+  if (warp == EPI_WARP0 && lane == 0) trace_stamp(p, 4);     // partial lists written
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) {
+    trace_stamp(p, 5);                                       // exit
+    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + 7] = clock64();
+  }
 }
 
 }  // namespace zs

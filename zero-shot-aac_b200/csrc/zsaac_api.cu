@@ -79,6 +79,7 @@ struct zs_ctx {
 
   int64_t launches = 0;
 
+  unsigned long long* trace = nullptr;  // zs_debug_trace: caller-owned [ctas, 8] device buffer
   bool profiling = false;          // zs_profile_enable
   cudaEvent_t* prof_ev = nullptr;  // 2 * ZS_PROFILE_RING events (start, stop)
   int prof_count = 0;              // launches recorded since enable (ring wraps)
@@ -138,6 +139,13 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
     const double cost = static_cast<double>(waves) * (tpc + 0.75);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s_eff; }
   }
+  if (const char* forced = getenv("ZSAAC_CHUNKS")) {   // tuning hook: pin the number of bank chunks
+    const int s = atoi(forced);
+    if (s >= 1 && s <= max_chunks) {
+      const int tpc = (pl.n_tiles + s - 1) / s;
+      best_s = (pl.n_tiles + tpc - 1) / tpc;
+    }
+  }
   pl.chunks = best_s;
   pl.tiles_per_chunk = (pl.n_tiles + best_s - 1) / best_s;
   const int64_t units = static_cast<int64_t>(pl.m_tiles) * pl.chunks;
@@ -145,11 +153,16 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
   return pl;
 }
 
+// Query workspace rows are padded to whole 256-row tile pairs (zero rows), so the query-side TMA
+// boxes are always fully inside the tensor (out-of-bounds boxes are served markedly slower).
+int64_t padded_query_rows(int64_t Q) { return (Q + 2 * zs::BLOCK_M - 1) / (2 * zs::BLOCK_M) * (2 * zs::BLOCK_M); }
+
 int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
-  if (Q > ctx->q_ws_rows) {
+  const int64_t q_pad = padded_query_rows(Q);
+  if (q_pad > ctx->q_ws_rows) {
     if (ctx->q_ws) { ZS_CUDA(cudaFree(ctx->q_ws)); ctx->q_ws = nullptr; ctx->q_ws_rows = 0; }
-    ZS_CUDA(cudaMalloc(&ctx->q_ws, static_cast<size_t>(Q) * ctx->bank_d * sizeof(__nv_bfloat16)));
-    ctx->q_ws_rows = Q;
+    ZS_CUDA(cudaMalloc(&ctx->q_ws, static_cast<size_t>(q_pad) * ctx->bank_d * sizeof(__nv_bfloat16)));
+    ctx->q_ws_rows = q_pad;
   }
   const Plan pl = make_plan(ctx, Q, k);
   const int64_t need = static_cast<int64_t>(pl.chunks) * zs::EPI_HALVES * Q * k;
@@ -165,11 +178,29 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
 }
 
 template <typename InT>
-void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int d, int normalize,
-                      cudaStream_t st) {
-  const int64_t blocks = (rows * 32 + 255) / 256;
+void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int64_t rows_out, int d,
+                      int normalize, cudaStream_t st) {
+  const int64_t blocks = (rows_out * 32 + 255) / 256;
   zs::normalize_cast_kernel<InT, __nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      static_cast<const InT*>(in), out, rows, d, normalize);
+      static_cast<const InT*>(in), out, rows, rows_out, d, normalize);
+}
+
+
+
+template <typename IdxT>
+void launch_merge(const float* scores, const IdxT* idx, int S, int64_t score_stride,
+                  int64_t index_stride, int64_t Q, int k, long long idx_offset, float* out_scores,
+                  long long* out_idx, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+  if (S <= 64)
+    zs::merge_lists_kernel<IdxT, 2><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
+                                                            Q, k, idx_offset, out_scores, out_idx);
+  else if (S <= 256)
+    zs::merge_lists_kernel<IdxT, 8><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
+                                                            Q, k, idx_offset, out_scores, out_idx);
+  else
+    zs::merge_lists_kernel<IdxT, 16><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
+                                                             Q, k, idx_offset, out_scores, out_idx);
 }
 
 template <int KCAP, int CG, bool DUMP>
@@ -220,11 +251,12 @@ int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkPara
 // Shared front half of zs_search / zs_debug_scores: cast queries, build the query map + params.
 int prepare_queries(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize,
                     CUtensorMap* qmap, cudaStream_t st) {
-  if (q_dtype == ZS_F32) launch_normalize<float>(queries, ctx->q_ws, Q, ctx->bank_d, normalize, st);
-  else launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, ctx->bank_d, normalize, st);
+  const int64_t q_pad = padded_query_rows(Q);
+  if (q_dtype == ZS_F32) launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
+  else launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
-  return encode_rows_map(ctx, qmap, ctx->q_ws, Q, ctx->bank_d, zs::BLOCK_M);
+  return encode_rows_map(ctx, qmap, ctx->q_ws, q_pad, ctx->bank_d, zs::BLOCK_M);
 }
 
 }  // namespace
@@ -335,8 +367,8 @@ int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* dst = ctx->bank + dst_row * ctx->bank_d;
-  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, ctx->bank_d, normalize, st);
-  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, ctx->bank_d, normalize, st);
+  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
+  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -435,15 +467,13 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   p.part_idx = ctx->part_idx;
   p.dump = nullptr;
   p.err_flag = ctx->err_flag;
+  p.trace = ctx->trace;
   rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
                     : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
   if (rc) return rc;
 
-  const int64_t blocks = (Q * 32 + 255) / 256;
-  zs::merge_lists_kernel<int><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k, Q, k, index_offset,
-      out_scores,
-      reinterpret_cast<long long*>(out_indices));
+  launch_merge<int>(ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k, Q, k,
+                    index_offset, out_scores, reinterpret_cast<long long*>(out_indices), st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -463,11 +493,9 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
     return fail(ZS_ERR_INVALID, "zs_merge: null pointer");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t blocks = (Q * 32 + 255) / 256;
-  zs::merge_lists_kernel<long long><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      scores, reinterpret_cast<const long long*>(indices), S, score_stride, index_stride, Q, k, 0ll,
-      out_scores,
-      reinterpret_cast<long long*>(out_indices));
+  launch_merge<long long>(scores, reinterpret_cast<const long long*>(indices), S, score_stride,
+                          index_stride, Q, k, 0ll, out_scores,
+                          reinterpret_cast<long long*>(out_indices), st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -501,9 +529,15 @@ int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (n_rows * 32 + 255) / 256;
-  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, d, 1);
+  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, n_rows, d, 1);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_debug_trace(zs_ctx* ctx, void* stamps) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_debug_trace: ctx is null");
+  ctx->trace = static_cast<unsigned long long*>(stamps);
   return ZS_OK;
 }
 

@@ -209,6 +209,12 @@ class RelatedBank:
                                      ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
 
+    def trace(self, stamps: Optional[torch.Tensor]) -> None:
+        """Per-CTA %globaltimer stamps of the fused kernel into a uint64-sized [ctas, 8] int64
+        tensor on this device (None switches tracing off).  Tuning hook."""
+        self._trace_keepalive = stamps
+        _abi.check(self._lib.zs_debug_trace(self._ctx, None if stamps is None else stamps.data_ptr()))
+
     def profile(self, enable: bool) -> None:
         """Bracket every fused-kernel launch with CUDA events (ring of 256 launches)."""
         _abi.check(self._lib.zs_profile_enable(self._ctx, 1 if enable else 0))
