@@ -74,7 +74,26 @@ struct SimTopkParams {
   float* dump;           // DUMP mode: [Q, n_bank]
   int* err_flag;
   unsigned long long* trace;  // nullable: [gridDim.x, 8] globaltimer stamps (zs_debug_trace)
+  // Soft lock-step of the bank stream (nullable = off).  All workers walk units of identical
+  // length in the same order, so "window w" (sync_window consecutive bank tiles of a unit
+  // iteration) covers the same tile positions for everyone.  A worker starts loading window w
+  // only after every worker has issued the loads of window w-1, which keeps the co-running
+  // workers within ~2 windows of each other: the bank tiles one worker pulled from HBM are still
+  // in L2 when the others ask for them.  Purely a performance hint: the wait is bounded and a
+  // worker that times out stops waiting (it keeps counting so nobody waits for it).
+  unsigned int* sync_cnt;     // [max_iters * windows_per_unit], zeroed by the host per launch
+  int sync_window;            // tiles per window
+  int windows_per_unit;       // ceil(tiles_per_chunk / sync_window)
+  int max_iters;              // ceil(num_units / num_workers)
 };
+
+constexpr long long SYNC_WAIT_LIMIT_CYCLES = 600000;   // ~0.3-0.4 ms: then give up lock-step
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void trace_stamp(const SimTopkParams& p, int slot) {
   if (p.trace != nullptr) {
@@ -196,7 +215,10 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if constexpr (CG == 2) {
         asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
       }
-      for (int u = worker; u < num_units; u += num_workers) {
+      const bool sync_on = (p.sync_cnt != nullptr) && is_leader;   // the leader paces the pair
+      bool sync_wait = sync_on;
+      int iter = 0;
+      for (int u = worker; u < num_units; u += num_workers, ++iter) {
         const int m_tile = u % p.num_m_tiles;
         const int chunk = u / p.num_m_tiles;
         const int t0 = chunk * p.tiles_per_chunk;
@@ -204,6 +226,17 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int q_row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M;
         for (int t = t0; t < t1; ++t) {
           const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
+          if (sync_on && (t - t0) % p.sync_window == 0) {
+            const int win = iter * p.windows_per_unit + (t - t0) / p.sync_window;
+            if (sync_wait && win > 0) {
+              const unsigned int* prev = p.sync_cnt + (win - 1);
+              const long long w0 = clock64();
+              while (ld_acquire_u32(prev) < static_cast<unsigned int>(num_workers)) {
+                if (clock64() - w0 > SYNC_WAIT_LIMIT_CYCLES) { sync_wait = false; break; }
+                __nanosleep(256);
+              }
+            }
+          }
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
             //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
@@ -223,7 +256,20 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+          if (sync_on && ((t - t0) % p.sync_window == p.sync_window - 1 || t == t1 - 1)) {
+            // loads of this window are issued: count this worker in
+            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + (t - t0) / p.sync_window, 1u);
+          }
         }
+        if (sync_on) {   // a ragged (shorter) last chunk: count the windows this unit does not have
+          for (int w = (t1 - t0 + p.sync_window - 1) / p.sync_window; w < p.windows_per_unit; ++w)
+            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
+        }
+      }
+      if (sync_on) {     // workers with one unit fewer: count the iterations they do not run
+        for (; iter < p.max_iters; ++iter)
+          for (int w = 0; w < p.windows_per_unit; ++w)
+            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
       }
     }
     __syncwarp();

@@ -76,6 +76,8 @@ struct zs_ctx {
   int* part_idx = nullptr;
   int64_t part_elems = 0;
   int* err_flag = nullptr;
+  unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
+  int64_t sync_cnt_elems = 0;
 
   int64_t launches = 0;
 
@@ -107,7 +109,10 @@ int kcap_for(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
 
 struct Plan {
   int cg, m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
+  int sync_window, windows_per_unit, max_iters;   // lock-step of the bank stream (0 = off)
 };
+
+constexpr int kSyncWindowTiles = 32;   // 32 tiles x 512 KiB = 16 MiB of bank per window
 
 // CTA pairs (cta_group::2, 256-row query tiles, half the shared-memory traffic per MMA) pay off
 // once there are several query tiles; a single 128-row tile streams the bank fastest from
@@ -149,7 +154,17 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
   pl.chunks = best_s;
   pl.tiles_per_chunk = (pl.n_tiles + best_s - 1) / best_s;
   const int64_t units = static_cast<int64_t>(pl.m_tiles) * pl.chunks;
-  pl.ctas = static_cast<int>(std::min<int64_t>(units, workers)) * cg;
+  const int n_workers = static_cast<int>(std::min<int64_t>(units, workers));
+  pl.ctas = n_workers * cg;
+  // Lock-step pays when several workers stream the same long chunk (m_tiles > 1) and the chunk
+  // is much larger than what stays in L2 between the fastest and the slowest worker.
+  const char* sync_env = getenv("ZSAAC_LOCKSTEP");
+  const bool sync_allowed = !(sync_env && sync_env[0] == '0');
+  if (sync_allowed && pl.m_tiles > 1 && n_workers > 1 && pl.tiles_per_chunk >= 4 * kSyncWindowTiles) {
+    pl.sync_window = kSyncWindowTiles;
+    pl.windows_per_unit = (pl.tiles_per_chunk + kSyncWindowTiles - 1) / kSyncWindowTiles;
+    pl.max_iters = static_cast<int>((units + n_workers - 1) / n_workers);
+  }
   return pl;
 }
 
@@ -165,6 +180,12 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
     ctx->q_ws_rows = q_pad;
   }
   const Plan pl = make_plan(ctx, Q, k);
+  const int64_t sync_need = static_cast<int64_t>(pl.max_iters) * pl.windows_per_unit;
+  if (sync_need > ctx->sync_cnt_elems) {
+    if (ctx->sync_cnt) { ZS_CUDA(cudaFree(ctx->sync_cnt)); ctx->sync_cnt = nullptr; ctx->sync_cnt_elems = 0; }
+    ZS_CUDA(cudaMalloc(&ctx->sync_cnt, static_cast<size_t>(sync_need) * sizeof(unsigned int)));
+    ctx->sync_cnt_elems = sync_need;
+  }
   const int64_t need = static_cast<int64_t>(pl.chunks) * zs::EPI_HALVES * Q * k;
   if (need > ctx->part_elems) {
     if (ctx->part_scores) { ZS_CUDA(cudaFree(ctx->part_scores)); ctx->part_scores = nullptr; }
@@ -317,6 +338,7 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->part_scores);
   cudaFree(ctx->part_idx);
   cudaFree(ctx->err_flag);
+  cudaFree(ctx->sync_cnt);
   if (ctx->prof_ev) {
     for (int i = 0; i < 2 * ZS_PROFILE_RING; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete[] ctx->prof_ev;
@@ -468,6 +490,14 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   p.dump = nullptr;
   p.err_flag = ctx->err_flag;
   p.trace = ctx->trace;
+  if (pl.sync_window > 0) {
+    const size_t n_cnt = static_cast<size_t>(pl.max_iters) * pl.windows_per_unit;
+    ZS_CUDA(cudaMemsetAsync(ctx->sync_cnt, 0, n_cnt * sizeof(unsigned int), st));
+    p.sync_cnt = ctx->sync_cnt;
+    p.sync_window = pl.sync_window;
+    p.windows_per_unit = pl.windows_per_unit;
+    p.max_iters = pl.max_iters;
+  }
   rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
                     : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
   if (rc) return rc;
