@@ -101,6 +101,20 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k,
               int normalize_queries, const int64_t* self_index, int64_t index_offset,
               float* out_scores, int64_t* out_indices, void* stream);
 
+/* Rank of ground-truth items (replaces the per-query `np.argsort(cos_sim(...))[::-1]` +
+ * `np.where(inds == i)` of the retrieval metrics a2t / t2a, reference
+ * retrieval/tools/utils.py:182-192,232-237).  Same GEMM as zs_search with a counting epilogue:
+ *   target_index  [Q, n_targets] int64 global bank indices (< 0 = unused slot)
+ *   out_ranks     [Q, n_targets] int64: number of bank rows, other than the target itself, whose
+ *                 similarity to query q is STRICTLY greater than the target's (0 = retrieved
+ *                 first); -1 for unused slots / targets outside this bank
+ *   out_target_scores  nullable [Q, n_targets] fp32 similarity of each target (+inf if unused)
+ * Exact score ties are resolved in the target's favour (np.argsort leaves them unspecified). */
+#define ZS_MAX_TARGETS 8
+int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize_queries,
+                  const int64_t* target_index, int n_targets, int64_t index_offset,
+                  float* out_target_scores, int64_t* out_ranks, void* stream);
+
 /* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
  * bank chunks) under the total order (score desc, index asc).
  *   scores  list s of query q starts at scores  + s*score_stride + q*k   (float elements)

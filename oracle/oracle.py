@@ -203,3 +203,62 @@ def check_topk(got_scores, got_indices, queries, bank, k, *, normalize=True, sel
                  and rep["all_clear_winners_present"] and rep["sorted"] and rep["distinct"]
                  and rep["in_range"])
     return rep
+
+
+# ------------------------------------------------------------------------------------------------
+# retrieval metrics — retrieval/tools/utils.py:169-251.  `util.cos_sim` comes from
+# sentence-transformers==2.2.2 (retrieval/work.yaml:159), absent from /root/reference; its
+# published definition is: normalise both operands along dim 1 (F.normalize, p=2), then mm.
+def cos_sim(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a = torch.as_tensor(a, dtype=torch.float32)
+    b = torch.as_tensor(b, dtype=torch.float32)
+    if a.dim() == 1:
+        a = a.unsqueeze(0)
+    if b.dim() == 1:
+        b = b.unsqueeze(0)
+    return torch.mm(F.normalize(a, p=2, dim=1), F.normalize(b, p=2, dim=1).transpose(0, 1))
+
+
+def _metric_summary(ranks: np.ndarray, ap10_sum: float):
+    r1 = 100.0 * len(np.where(ranks < 1)[0]) / len(ranks)
+    r5 = 100.0 * len(np.where(ranks < 5)[0]) / len(ranks)
+    r10 = 100.0 * len(np.where(ranks < 10)[0]) / len(ranks)
+    r50 = 100.0 * len(np.where(ranks < 50)[0]) / len(ranks)
+    return (r1, r5, r10, r50, np.floor(np.median(ranks)) + 1, ranks.mean() + 1,
+            100.0 * ap10_sum / len(ranks))
+
+
+def a2t(audio_embs, cap_embs):
+    """Literal restatement of utils.py:169-213; returns (metrics tuple, ranks, top1, positions)."""
+    num_audios = int(audio_embs.shape[0] / 5)
+    ranks, top1, AP10 = np.zeros(num_audios), np.zeros(num_audios), np.zeros(num_audios)
+    positions = np.zeros((num_audios, 5), np.int64)
+    for index in range(num_audios):
+        d = cos_sim(torch.Tensor(audio_embs[5 * index]), torch.Tensor(cap_embs)).squeeze(0).numpy()  # :182
+        inds = np.argsort(d)[::-1]                                                                    # :183
+        inds_map, rank = [], 1e20
+        for slot, i in enumerate(range(5 * index, 5 * index + 5)):
+            tmp = np.where(inds == i)[0][0]                                                           # :189
+            positions[index, slot] = tmp
+            rank = min(rank, tmp)
+            if tmp < 10:
+                inds_map.append(tmp + 1)
+        inds_map = np.sort(np.array(inds_map))
+        AP10[index] = np.sum(np.arange(1, len(inds_map) + 1) / inds_map) / 5 if len(inds_map) else 0.0
+        ranks[index], top1[index] = rank, inds[0]
+    return _metric_summary(ranks, float(np.sum(AP10))), ranks, top1, positions
+
+
+def t2a(audio_embs, cap_embs):
+    """Literal restatement of utils.py:216-251; returns (metrics tuple, ranks, top1)."""
+    num_audios = int(audio_embs.shape[0] / 5)
+    audios = np.array([audio_embs[i] for i in range(0, audio_embs.shape[0], 5)])
+    ranks, top1 = np.zeros(5 * num_audios), np.zeros(5 * num_audios)
+    for index in range(num_audios):
+        d = cos_sim(torch.Tensor(cap_embs[5 * index: 5 * index + 5]), torch.Tensor(audios)).numpy()   # :232
+        for i in range(d.shape[0]):
+            inds = np.argsort(d[i])[::-1]
+            ranks[5 * index + i] = np.where(inds == index)[0][0]                                      # :237
+            top1[5 * index + i] = inds[0]
+    ap10_sum = float(np.sum(1 / (ranks[np.where(ranks < 10)[0]] + 1)))
+    return _metric_summary(ranks, ap10_sum), ranks, top1

@@ -156,7 +156,59 @@ def run_sec_case(name, case):
     print(f"{name}: index[0]={idx[0].tolist()}")
 
 
+RETRIEVAL_CASES = {
+    "retrieval_metrics": dict(seed=3001, audios=60, clusters=6, sigma_in=0.5, noise=6.0),
+    "retrieval_metrics_easy": dict(seed=3002, audios=37, clusters=37, sigma_in=0.0, noise=0.9),
+}
+
+
+def make_retrieval_inputs(case):
+    """CLAP-like pairs: clustered audio embeddings, each with 5 noisy caption embeddings, noisy
+    enough that the ground truth is not always retrieved first."""
+    rs = np.random.RandomState(case["seed"])
+    c = rs.standard_normal((case["clusters"], D)).astype(np.float32)
+    a = c[rs.randint(0, case["clusters"], size=case["audios"])] \
+        + case["sigma_in"] * rs.standard_normal((case["audios"], D)).astype(np.float32)
+    audio_embs = np.repeat(a, 5, axis=0)                      # reference layout: audio repeated 5x
+    cap_embs = audio_embs + case["noise"] * rs.standard_normal(audio_embs.shape).astype(np.float32)
+    return audio_embs, cap_embs
+
+
+def run_retrieval_case(name, case):
+    # sentence-transformers is not installed: provide util.cos_sim per its published definition
+    # (normalise both operands, mm) so that the reference module imports and runs unmodified
+    import types
+    st = types.ModuleType("sentence_transformers")
+    st_util = types.ModuleType("sentence_transformers.util")
+
+    def cos_sim(a, b):
+        a = torch.as_tensor(a, dtype=torch.float32)
+        b = torch.as_tensor(b, dtype=torch.float32)
+        if a.dim() == 1:
+            a = a.unsqueeze(0)
+        if b.dim() == 1:
+            b = b.unsqueeze(0)
+        return torch.mm(torch.nn.functional.normalize(a, p=2, dim=1),
+                        torch.nn.functional.normalize(b, p=2, dim=1).transpose(0, 1))
+
+    st_util.cos_sim = cos_sim
+    st.util = st_util
+    sys.modules.setdefault("sentence_transformers", st)
+    sys.modules.setdefault("sentence_transformers.util", st_util)
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    ref = load_ref_module("retrieval/tools/utils.py", "ref_retrieval_utils")
+    audio_embs, cap_embs = make_retrieval_inputs(case)
+    a = ref.a2t(audio_embs, cap_embs, return_ranks=True)
+    t = ref.t2a(audio_embs, cap_embs, return_ranks=True)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                        a2t_metrics=np.array(a[:7], np.float64), a2t_ranks=a[7], a2t_top1=a[8],
+                        t2a_metrics=np.array(t[:7], np.float64), t2a_ranks=t[7], t2a_top1=t[8])
+    print(f"{name}: a2t {np.round(a[:7], 2)} t2a {np.round(t[:7], 2)}")
+
+
 if __name__ == "__main__":
+    for n, c in RETRIEVAL_CASES.items():
+        run_retrieval_case(n, c)
     for n, c in CASES.items():
         run_generator_case(n, c)
     for n, c in SEC_CASES.items():

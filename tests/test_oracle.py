@@ -131,3 +131,20 @@ def test_check_topk_flags_wrong_answers():
     bad_i[0, 0] = (i[0, 0] + 1) % 50 if ((i[0, 0] + 1) % 50) not in i[0].tolist() else (i[0, 0] + 7) % 50
     assert not oracle.check_topk(s, bad_i, q, b, 5)["ok"]
     assert not oracle.check_topk(s + 0.01, i, q, b, 5)["ok"]
+
+
+@pytest.mark.parametrize("name", list(recipes.RETRIEVAL_CASES))
+def test_retrieval_metrics_match_reference_golden(name):
+    """a2t / t2a restated (oracle) vs the reference's own functions (golden)."""
+    audio, caps = recipes.make_retrieval_inputs(recipes.RETRIEVAL_CASES[name])
+    g = helpers.golden(name)
+    m, ranks, top1, positions = oracle.a2t(audio, caps)
+    np.testing.assert_allclose(np.array(m, np.float64), g["a2t_metrics"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(ranks, g["a2t_ranks"])
+    np.testing.assert_array_equal(top1, g["a2t_top1"])
+    assert (positions.min(axis=1) == ranks).all()
+    m, ranks, top1 = oracle.t2a(audio, caps)
+    np.testing.assert_allclose(np.array(m, np.float64), g["t2a_metrics"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(ranks, g["t2a_ranks"])
+    np.testing.assert_array_equal(top1, g["t2a_top1"])
+    assert 0 < g["a2t_metrics"][0] < 100 and 0 < g["t2a_metrics"][0] < 100   # a non-trivial fixture

@@ -170,6 +170,59 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rank-of-target support (retrieval metrics a2t / t2a, reference retrieval/tools/utils.py:169-251)
+
+// One warp per (query, target): score = <bf16 query row, bf16 bank row> in fp32, i.e. the same
+// operands the fused kernel multiplies (accumulation order differs, which only matters for
+// candidates within an ulp of the target; the kernel never counts the target against itself).
+// Also converts the global target index to a column of this bank (-1 = absent / unused).
+__global__ void __launch_bounds__(256)
+target_scores_kernel(const __nv_bfloat16* __restrict__ queries, const __nv_bfloat16* __restrict__ bank,
+                     const long long* __restrict__ target_index, int64_t n_pairs, int n_targets,
+                     int d, long long index_offset, int64_t n_bank, float* __restrict__ out_scores,
+                     int* __restrict__ out_cols) {
+  const int64_t pair = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;
+  const int64_t q = pair / n_targets;
+  const long long g = target_index[pair];
+  const long long col = g - index_offset;
+  if (g < 0 || col < 0 || col >= n_bank) {
+    if (lane == 0) { out_scores[pair] = CUDART_INF_F; out_cols[pair] = -1; }
+    return;
+  }
+  const __nv_bfloat16* a = queries + q * d;
+  const __nv_bfloat16* b = bank + col * d;
+  float acc = 0.0f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const uint2 ra = *reinterpret_cast<const uint2*>(a + c);
+    const uint2 rb = *reinterpret_cast<const uint2*>(b + c);
+    const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&ra.x);
+    const __nv_bfloat162 a1 = *reinterpret_cast<const __nv_bfloat162*>(&ra.y);
+    const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&rb.x);
+    const __nv_bfloat162 b1 = *reinterpret_cast<const __nv_bfloat162*>(&rb.y);
+    acc = fmaf(__low2float(a0), __low2float(b0), acc);
+    acc = fmaf(__high2float(a0), __high2float(b0), acc);
+    acc = fmaf(__low2float(a1), __low2float(b1), acc);
+    acc = fmaf(__high2float(a1), __high2float(b1), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) { out_scores[pair] = acc; out_cols[pair] = static_cast<int>(col); }
+}
+
+// ranks[i] = sum over the partial lists of counts[list, i]; absent targets get -1.
+__global__ void __launch_bounds__(256)
+sum_counts_kernel(const int* __restrict__ part_counts, int n_lists, int64_t n_pairs,
+                  const int* __restrict__ cols, long long* __restrict__ out_ranks) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  if (cols[i] < 0) { out_ranks[i] = -1; return; }
+  long long total = 0;
+  for (int l = 0; l < n_lists; ++l) total += part_counts[static_cast<int64_t>(l) * n_pairs + i];
+  out_ranks[i] = total;
+}
+
 // One warp per output row, 16-byte vectors.  Out-of-range indices produce a zero row.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ src, int64_t n_src_rows, int d,

@@ -72,6 +72,12 @@ struct SimTopkParams {
   float* part_scores;    // [num_chunks * EPI_HALVES, Q, k]
   int* part_idx;         // [num_chunks * EPI_HALVES, Q, k]  column within the shard
   float* dump;           // DUMP mode: [Q, n_bank]
+  // RANK mode: per (row, target) the target's score and column within the shard (-1 = unused),
+  // and the per-(chunk, half) partial counts
+  const float* tgt_scores;   // [Q, n_targets]
+  const int* tgt_cols;       // [Q, n_targets]
+  int n_targets;
+  int* part_counts;          // [num_chunks * EPI_HALVES, Q, n_targets]
   int* err_flag;
   unsigned long long* trace;  // nullable: [gridDim.x, 8] globaltimer stamps (zs_debug_trace)
   // Soft lock-step of the bank stream (nullable = off).  All workers walk units of identical
@@ -151,10 +157,18 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
-template <int KCAP, int CG, bool DUMP>
+// MODE_TOPK: running top-k (KCAP list slots).  MODE_DUMP: write the score matrix (test hook).
+// MODE_RANK: count, per query row and per target (KCAP = max targets per row), the bank rows
+// whose score is strictly greater than the target's score — the rank of the ground truth that
+// the reference's retrieval metrics obtain from a full argsort (retrieval/tools/utils.py:183,236).
+enum : int { MODE_TOPK = 0, MODE_DUMP = 1, MODE_RANK = 2 };
+
+template <int KCAP, int CG, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const SimTopkParams p) {
+  constexpr bool DUMP = (MODE == MODE_DUMP);
+  constexpr bool RANK = (MODE == MODE_RANK);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -327,13 +341,29 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
       const int row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M + row_in_tile;
       int self_col = -1;
-      if (!DUMP && p.self_index != nullptr && row < p.Q) {
+      if (MODE == MODE_TOPK && p.self_index != nullptr && row < p.Q) {
         const long long g = p.self_index[row];
         const long long c = g - p.index_offset;
         if (g >= 0 && c >= 0 && c < p.n_bank) self_col = static_cast<int>(c);
       }
       list.init(p.k);
       float thr = list.threshold();
+      // RANK mode state (KCAP = target slots)
+      float ts[KCAP];
+      int tc[KCAP];
+      int cnt[KCAP];
+      if constexpr (RANK) {
+#pragma unroll
+        for (int g = 0; g < KCAP; ++g) {
+          ts[g] = CUDART_INF_F;      // nothing is greater than +inf: unused slots count 0
+          tc[g] = -1;
+          cnt[g] = 0;
+          if (row < p.Q && g < p.n_targets) {
+            tc[g] = p.tgt_cols[static_cast<size_t>(row) * p.n_targets + g];
+            if (tc[g] >= 0) ts[g] = p.tgt_scores[static_cast<size_t>(row) * p.n_targets + g];
+          }
+        }
+      }
       for (int t = t0; t < t1; ++t, ++tile_count) {
         const uint32_t acc = tile_count & 1u;
         const uint32_t acc_phase = (tile_count >> 1) & 1u;
@@ -354,6 +384,31 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n_bank)
                   p.dump[static_cast<size_t>(row) * p.n_bank + col0 + j] = __uint_as_float(r[j]);
+            }
+          } else if constexpr (RANK) {
+            if (col0 + 32 <= p.n_bank) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]);
+#pragma unroll
+                for (int g = 0; g < KCAP; ++g) cnt[g] += (v > ts[g]) ? 1 : 0;
+              }
+            } else {   // ragged bank tail: zero-filled columns beyond the bank do not count
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]);
+                const bool valid = col0 + j < p.n_bank;
+#pragma unroll
+                for (int g = 0; g < KCAP; ++g) cnt[g] += (valid && v > ts[g]) ? 1 : 0;
+              }
+            }
+            // a target never counts against itself, whatever the rounding of its own MMA score
+#pragma unroll
+            for (int g = 0; g < KCAP; ++g) {
+              if (tc[g] >= col0 && tc[g] < col0 + 32) {
+                const float own = __uint_as_float(select32(r, tc[g] - col0));
+                if (own > ts[g]) cnt[g] -= 1;
+              }
             }
           } else {
             // fast path: two instructions per score, no branch
@@ -386,7 +441,15 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
       if (warp == EPI_WARP0 && lane == 0) trace_stamp(p, 3);   // last tile of the unit scanned
-      if constexpr (!DUMP) {
+      if constexpr (RANK) {
+        if (row < p.Q) {
+          const size_t o = (static_cast<size_t>(chunk * EPI_HALVES + half) * p.Q + row) * p.n_targets;
+#pragma unroll
+          for (int g = 0; g < KCAP; ++g)
+            if (g < p.n_targets) p.part_counts[o + g] = cnt[g];
+        }
+      }
+      if constexpr (MODE == MODE_TOPK) {
         if (row < p.Q) {
           const size_t o = (static_cast<size_t>(chunk * EPI_HALVES + half) * p.Q + row) * p.k;
           const int pinned = KCAP - p.k;   // slots [pinned, KCAP) are the live entries

@@ -76,6 +76,10 @@ struct zs_ctx {
   int* part_idx = nullptr;
   int64_t part_elems = 0;
   int* err_flag = nullptr;
+  float* tgt_scores = nullptr;        // rank mode: [Q, T]
+  int* tgt_cols = nullptr;
+  int* part_counts = nullptr;         // [chunks * EPI_HALVES, Q, T]
+  int64_t tgt_elems = 0, count_elems = 0;
   unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
   int64_t sync_cnt_elems = 0;
 
@@ -224,10 +228,10 @@ void launch_merge(const float* scores, const IdxT* idx, int S, int64_t score_str
                                                              Q, k, idx_offset, out_scores, out_idx);
 }
 
-template <int KCAP, int CG, bool DUMP>
+template <int KCAP, int CG, int MODE>
 int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
                    cudaStream_t st) {
-  auto kern = zs::zs_simtopk_kernel<KCAP, CG, DUMP>;
+  auto kern = zs::zs_simtopk_kernel<KCAP, CG, MODE>;
   const int smem = zs::smem_bytes<CG>();
   ZS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
@@ -246,7 +250,7 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  const bool prof = ctx->profiling && !DUMP;
+  const bool prof = ctx->profiling && MODE != zs::MODE_DUMP;
   const int slot = ctx->prof_count % ZS_PROFILE_RING;
   if (prof) ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot], st));
   ZS_CUDA(cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p));
@@ -261,11 +265,14 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
 template <int CG>
 int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
                      bool dump, cudaStream_t st) {
-  if (dump) return launch_simtopk<8, CG, true>(ctx, qmap, p, ctas, st);
+  if (dump) return launch_simtopk<8, CG, zs::MODE_DUMP>(ctx, qmap, p, ctas, st);
+  if (p.part_counts != nullptr)   // rank mode: KCAP = target slots
+    return p.n_targets <= 1 ? launch_simtopk<1, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st)
+                            : launch_simtopk<8, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st);
   switch (kcap_for(p.k)) {
-    case 8: return launch_simtopk<8, CG, false>(ctx, qmap, p, ctas, st);
-    case 16: return launch_simtopk<16, CG, false>(ctx, qmap, p, ctas, st);
-    default: return launch_simtopk<32, CG, false>(ctx, qmap, p, ctas, st);
+    case 8: return launch_simtopk<8, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
+    case 16: return launch_simtopk<16, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
+    default: return launch_simtopk<32, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
   }
 }
 
@@ -339,6 +346,9 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->part_idx);
   cudaFree(ctx->err_flag);
   cudaFree(ctx->sync_cnt);
+  cudaFree(ctx->tgt_scores);
+  cudaFree(ctx->tgt_cols);
+  cudaFree(ctx->part_counts);
   if (ctx->prof_ev) {
     for (int i = 0; i < 2 * ZS_PROFILE_RING; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete[] ctx->prof_ev;
@@ -506,6 +516,82 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
                     index_offset, out_scores, reinterpret_cast<long long*>(out_indices), st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
+  return ZS_OK;
+}
+
+int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize_queries,
+                  const int64_t* target_index, int n_targets, int64_t index_offset,
+                  float* out_target_scores, int64_t* out_ranks, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_rank_count: ctx is null");
+  if (!ctx->bank) return fail(ZS_ERR_STATE, "zs_rank_count: no bank uploaded");
+  if (Q < 0 || Q > 0x7fffff00ll) return fail(ZS_ERR_INVALID, "zs_rank_count: Q=%lld", (long long)Q);
+  if (n_targets < 1 || n_targets > ZS_MAX_TARGETS)
+    return fail(ZS_ERR_INVALID, "zs_rank_count: n_targets=%d outside [1, %d]", n_targets, ZS_MAX_TARGETS);
+  if (q_dtype != ZS_F32 && q_dtype != ZS_BF16)
+    return fail(ZS_ERR_INVALID, "zs_rank_count: unknown query dtype %d", q_dtype);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !target_index || !out_ranks)
+    return fail(ZS_ERR_INVALID, "zs_rank_count: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_workspace(ctx, Q, 1);
+  if (rc) return rc;
+  const Plan pl = make_plan(ctx, Q, 1);
+  const int64_t n_pairs = Q * n_targets;
+  const int n_lists = pl.chunks * zs::EPI_HALVES;
+  if (n_pairs > ctx->tgt_elems) {
+    if (ctx->tgt_scores) { ZS_CUDA(cudaFree(ctx->tgt_scores)); ctx->tgt_scores = nullptr; }
+    if (ctx->tgt_cols) { ZS_CUDA(cudaFree(ctx->tgt_cols)); ctx->tgt_cols = nullptr; }
+    ctx->tgt_elems = 0;
+    ZS_CUDA(cudaMalloc(&ctx->tgt_scores, static_cast<size_t>(n_pairs) * sizeof(float)));
+    ZS_CUDA(cudaMalloc(&ctx->tgt_cols, static_cast<size_t>(n_pairs) * sizeof(int)));
+    ctx->tgt_elems = n_pairs;
+  }
+  if (n_pairs * n_lists > ctx->count_elems) {
+    if (ctx->part_counts) { ZS_CUDA(cudaFree(ctx->part_counts)); ctx->part_counts = nullptr; }
+    ctx->count_elems = 0;
+    ZS_CUDA(cudaMalloc(&ctx->part_counts, static_cast<size_t>(n_pairs) * n_lists * sizeof(int)));
+    ctx->count_elems = n_pairs * n_lists;
+  }
+  CUtensorMap qmap;
+  rc = prepare_queries(ctx, queries, Q, q_dtype, normalize_queries, &qmap, st);
+  if (rc) return rc;
+  {
+    const int64_t blocks = (n_pairs * 32 + 255) / 256;
+    zs::target_scores_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        ctx->q_ws, ctx->bank, reinterpret_cast<const long long*>(target_index), n_pairs, n_targets,
+        ctx->bank_d, index_offset, ctx->bank_rows, ctx->tgt_scores, ctx->tgt_cols);
+    ZS_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  zs::SimTopkParams p{};
+  p.Q = static_cast<int>(Q);
+  p.n_bank = static_cast<int>(ctx->bank_rows);
+  p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
+  p.num_m_tiles = pl.m_tiles;
+  p.num_n_tiles = pl.n_tiles;
+  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.num_chunks = pl.chunks;
+  p.k = 1;
+  p.index_offset = index_offset;
+  p.err_flag = ctx->err_flag;
+  p.tgt_scores = ctx->tgt_scores;
+  p.tgt_cols = ctx->tgt_cols;
+  p.n_targets = n_targets;
+  p.part_counts = ctx->part_counts;
+  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
+                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  if (rc) return rc;
+  {
+    const int64_t blocks = (n_pairs + 255) / 256;
+    zs::sum_counts_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        ctx->part_counts, n_lists, n_pairs, ctx->tgt_cols, reinterpret_cast<long long*>(out_ranks));
+    ZS_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  if (out_target_scores)
+    ZS_CUDA(cudaMemcpyAsync(out_target_scores, ctx->tgt_scores, static_cast<size_t>(n_pairs) * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
   return ZS_OK;
 }
 

@@ -138,6 +138,37 @@ class RelatedBank:
                 scores.data_ptr(), indices.data_ptr(), _stream_ptr(self.device)))
         return scores, indices
 
+    def rank_of(self, queries: torch.Tensor, targets: torch.Tensor, *, normalize_queries: bool = True
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rank of given bank rows in every query's similarity ordering, without sorting.
+
+        targets [Q, T] (T <= 8) int64 global bank indices (< 0 = unused slot).  Returns
+        (ranks [Q, T] int64, target_scores [Q, T] float32): ranks[q, t] = number of other bank
+        rows scoring strictly higher than targets[q, t] for query q (0 = retrieved first; -1 for
+        unused slots).  Same fused GEMM as search() with a counting epilogue.
+        """
+        if queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {tuple(queries.shape)}")
+        if queries.device != self.device:
+            raise ValueError(f"queries are on {queries.device}, the bank is on {self.device}")
+        queries = queries.detach().contiguous()
+        q = queries.shape[0]
+        targets = targets.detach().to(device=self.device, dtype=torch.int64)
+        if targets.dim() == 1:
+            targets = targets.unsqueeze(1)
+        if targets.dim() != 2 or targets.shape[0] != q:
+            raise ValueError(f"targets must be [{q}, T], got {tuple(targets.shape)}")
+        targets = targets.contiguous()
+        t = targets.shape[1]
+        ranks = torch.empty((q, t), dtype=torch.int64, device=self.device)
+        scores = torch.empty((q, t), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_rank_count(
+                self._ctx, queries.data_ptr(), q, _dtype_code(queries), 1 if normalize_queries else 0,
+                targets.data_ptr(), t, self.index_offset, scores.data_ptr(), ranks.data_ptr(),
+                _stream_ptr(self.device)))
+        return ranks, scores
+
     def debug_scores(self, queries: torch.Tensor, *, normalize_queries: bool = True) -> torch.Tensor:
         """Full [Q, rows] similarity matrix out of the same tcgen05 pipeline (tests only)."""
         queries = queries.detach().contiguous()
