@@ -10,6 +10,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "ptx_sm100.cuh"
+
 namespace zs {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -26,6 +28,9 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
                       int64_t n_rows_out, int d, int normalize) {
+  // the consumer (fused search kernel) may begin its prologue now; it waits for this grid to
+  // finish before it reads `out`
+  ptx::pdl_launch_dependents();
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows_out) return;
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(256)
 merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
                    int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
                    float* __restrict__ out_scores, long long* __restrict__ out_idx) {
+  ptx::pdl_wait();   // lists are written by the preceding grid (no-op without the PDL attribute)
   const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;

@@ -213,6 +213,9 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   if (threadIdx.x == 0) trace_stamp(p, 1);               // barriers + TMEM ready
+  // Everything above overlaps the tail of the query normalise/cast kernel (programmatic
+  // dependent launch); its output (the bf16 query workspace) is only touched below.
+  ptx::pdl_wait();
 
   // static persistent schedule: all roles walk the same unit list
   const int worker = static_cast<int>(blockIdx.x) / CG;
@@ -466,6 +469,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 
   if (warp == EPI_WARP0 && lane == 0) trace_stamp(p, 4);     // partial lists written
+  if (threadIdx.x == 0) ptx::pdl_launch_dependents();        // the merge kernel may start its prologue
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);

@@ -86,6 +86,8 @@ struct zs_ctx {
   int64_t launches = 0;
 
   unsigned long long* trace = nullptr;  // zs_debug_trace: caller-owned [ctas, 8] device buffer
+  bool pdl_enabled = true;         // env ZSAAC_PDL=0 switches programmatic dependent launch off
+  bool pdl_next = false;           // next fused-kernel launch directly follows its producer kernel
   bool profiling = false;          // zs_profile_enable
   cudaEvent_t* prof_ev = nullptr;  // 2 * ZS_PROFILE_RING events (start, stop)
   int prof_count = 0;              // launches recorded since enable (ring wraps)
@@ -212,20 +214,30 @@ void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int64_t 
 
 
 
+// pdl: launch as a programmatic dependent of the kernel enqueued just before (its prologue may
+// overlap that kernel's tail; merge_lists_kernel waits with griddepcontrol.wait before reading)
 template <typename IdxT>
-void launch_merge(const float* scores, const IdxT* idx, int S, int64_t score_stride,
-                  int64_t index_stride, int64_t Q, int k, long long idx_offset, float* out_scores,
-                  long long* out_idx, cudaStream_t st) {
-  const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t score_stride,
+                         int64_t index_stride, int64_t Q, int k, long long idx_offset,
+                         float* out_scores, long long* out_idx, bool pdl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>((Q * 32 + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (S <= 64)
-    zs::merge_lists_kernel<IdxT, 2><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
-                                                            Q, k, idx_offset, out_scores, out_idx);
-  else if (S <= 256)
-    zs::merge_lists_kernel<IdxT, 8><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
-                                                            Q, k, idx_offset, out_scores, out_idx);
-  else
-    zs::merge_lists_kernel<IdxT, 16><<<blocks, 256, 0, st>>>(scores, idx, S, score_stride, index_stride,
-                                                             Q, k, idx_offset, out_scores, out_idx);
+    return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 2>, scores, idx, S, score_stride,
+                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+  if (S <= 256)
+    return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 8>, scores, idx, S, score_stride,
+                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+  return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 16>, scores, idx, S, score_stride,
+                            index_stride, Q, k, idx_offset, out_scores, out_idx);
 }
 
 template <int KCAP, int CG, int MODE>
@@ -239,14 +251,19 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   cfg.blockDim = dim3(zs::NUM_THREADS);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int n_attr = 0;
   if (CG == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    n_attr = 1;
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (ctx->pdl_next) {   // the query normalise/cast kernel was enqueued just before this launch
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
@@ -327,6 +344,8 @@ int zs_create(zs_ctx** out, int device) {
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   const char* cg = getenv("ZSAAC_CTA_GROUP");
   if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group_override = cg[0] - '0';
+  const char* pdl = getenv("ZSAAC_PDL");
+  if (pdl && pdl[0] == '0') ctx->pdl_enabled = false;
   e = cudaMalloc(&ctx->err_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->err_flag, 0, sizeof(int));
   if (e != cudaSuccess) {
@@ -479,11 +498,15 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_workspace(ctx, Q, k);
   if (rc) return rc;
+  const Plan pl = make_plan(ctx, Q, k);
+  if (pl.sync_window > 0) {   // before the cast kernel, so that cast -> fused kernel stay adjacent
+    const size_t n_cnt = static_cast<size_t>(pl.max_iters) * pl.windows_per_unit;
+    ZS_CUDA(cudaMemsetAsync(ctx->sync_cnt, 0, n_cnt * sizeof(unsigned int), st));
+  }
   CUtensorMap qmap;
   rc = prepare_queries(ctx, queries, Q, q_dtype, normalize_queries, &qmap, st);
   if (rc) return rc;
 
-  const Plan pl = make_plan(ctx, Q, k);
   zs::SimTopkParams p{};
   p.Q = static_cast<int>(Q);
   p.n_bank = static_cast<int>(ctx->bank_rows);
@@ -501,20 +524,22 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   p.err_flag = ctx->err_flag;
   p.trace = ctx->trace;
   if (pl.sync_window > 0) {
-    const size_t n_cnt = static_cast<size_t>(pl.max_iters) * pl.windows_per_unit;
-    ZS_CUDA(cudaMemsetAsync(ctx->sync_cnt, 0, n_cnt * sizeof(unsigned int), st));
     p.sync_cnt = ctx->sync_cnt;
     p.sync_window = pl.sync_window;
     p.windows_per_unit = pl.windows_per_unit;
     p.max_iters = pl.max_iters;
   }
+  // programmatic dependent launch: cast kernel -> fused kernel -> merge (not while profiling,
+  // the timing events would sit between the kernels)
+  ctx->pdl_next = ctx->pdl_enabled && !ctx->profiling;
   rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
                     : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  ctx->pdl_next = false;
   if (rc) return rc;
 
-  launch_merge<int>(ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k, Q, k,
-                    index_offset, out_scores, reinterpret_cast<long long*>(out_indices), st);
-  ZS_CUDA(cudaGetLastError());
+  ZS_CUDA(launch_merge<int>(ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k,
+                            Q, k, index_offset, out_scores, reinterpret_cast<long long*>(out_indices),
+                            /*pdl=*/ctx->pdl_enabled && !ctx->profiling, st));
   ctx->launches += 1;
   return ZS_OK;
 }
@@ -609,10 +634,9 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
     return fail(ZS_ERR_INVALID, "zs_merge: null pointer");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  launch_merge<long long>(scores, reinterpret_cast<const long long*>(indices), S, score_stride,
-                          index_stride, Q, k, 0ll, out_scores,
-                          reinterpret_cast<long long*>(out_indices), st);
-  ZS_CUDA(cudaGetLastError());
+  ZS_CUDA(launch_merge<long long>(scores, reinterpret_cast<const long long*>(indices), S, score_stride,
+                                  index_stride, Q, k, 0ll, out_scores,
+                                  reinterpret_cast<long long*>(out_indices), /*pdl=*/false, st));
   ctx->launches += 1;
   return ZS_OK;
 }
