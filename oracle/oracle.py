@@ -46,13 +46,16 @@ def normalize_rows(x: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------
 # the hot loop, literally — data_handing/embeddings_related_generator.py:19-28
-def process_data_literal(valid_text_embs: torch.Tensor, all_data: List[dict], topnumber: int
-                         ) -> Iterator[dict]:
-    """One query per iteration exactly as the reference writes it (CPU instead of 'cuda')."""
+def process_data_literal(valid_text_embs: torch.Tensor, all_data: List[dict], topnumber: int,
+                         device: str = "cpu") -> Iterator[dict]:
+    """One query per iteration exactly as the reference writes it.  device='cuda' reproduces the
+    reference's own device placement (bank on the GPU, per-item H2D / D2H); the default 'cpu' is
+    what the build container can run."""
+    valid_text_embs = valid_text_embs.to(device)
     for item in all_data:
-        text_embs = F.normalize(item["text_embedding"].cpu().float(), dim=-1)            # :21
+        text_embs = F.normalize(item["text_embedding"].cpu().float(), dim=-1).to(device)   # :21
         ids = torch.cosine_similarity(text_embs, valid_text_embs).topk(topnumber)[1]    # :22
-        related_embs = valid_text_embs[ids]                                             # :23
+        related_embs = valid_text_embs[ids.cpu()].cpu()                                 # :23
         item["text_embedding"] = item["text_embedding"].cpu()                           # :25
         item["related_embeddings"] = related_embs                                       # :26
         yield item

@@ -291,3 +291,49 @@ def test_wavcaps_scale_properties(zs):
     assert rep["ok"], rep
     rb.close()
     rbp.close()
+
+
+# ---------------------------------------------------------------- adversarial orderings / hypothesis
+def test_adversarially_ordered_bank(zs, cta_group):
+    """Bank sorted by similarity to the queries: ascending order makes EVERY score a new maximum
+    (every element takes the insert path), descending order makes none after the first k."""
+    base = helpers.seeded((1, 1024), 301)
+    noise = helpers.seeded((6000, 1024), 302)
+    w = torch.linspace(0.0, 3.0, 6000).unsqueeze(1)          # row j is closer to `base` as j grows
+    asc = noise + w * base
+    q = base + 0.05 * helpers.seeded((40, 1024), 303)
+    for bank in (asc, asc.flip(0)):
+        for k in (1, 10, 32):
+            s, i = run_search(zs, q, bank, k)
+            rep = oracle.check_topk(s, i, q, bank, k)
+            assert rep["ok"], (k, rep)
+
+
+def test_constant_scores_everywhere(zs):
+    """All bank rows identical: every score ties, the answer is the first k indices."""
+    row = helpers.seeded((1, 1024), 311)
+    bank = row.expand(1000, 1024).contiguous()
+    q = helpers.seeded((3, 1024), 312)
+    s, i = run_search(zs, q, bank, 7)
+    assert torch.equal(i, torch.arange(7).expand(3, 7))
+    assert (s == s[:, :1]).all()
+
+
+def test_random_shapes_property(zs):
+    """Random (Q, N, k, offsets) against the oracle; hypothesis drives the shapes."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(q=st.integers(1, 400), n=st.integers(1, 3000), k=st.integers(1, 32),
+           off=st.integers(0, 10_000_000), seed=st.integers(0, 10_000))
+    def check(q, n, k, off, seed):
+        k = min(k, n)
+        qs, bank = helpers.seeded((q, 1024), seed), helpers.seeded((n, 1024), seed + 1)
+        rb = zs.RelatedBank.from_tensor(bank.cuda(), index_offset=off)
+        s, i = rb.search(qs.cuda(), k)
+        torch.cuda.synchronize()
+        rb.close()
+        rep = oracle.check_topk(s.cpu(), i.cpu() - off, qs, bank, k)
+        assert rep["ok"], (q, n, k, off, rep)
+
+    check()

@@ -111,3 +111,27 @@ def test_shard_bounds_cover_the_bank_exactly():
         per = -(-n // w)
         assert all(hi - lo <= per for lo, hi in b)
     assert shard_bounds(10_000_000, 8)[3] == (3_750_000, 5_000_000)
+
+
+def test_parallel_writer_emits_the_same_bytes_as_the_serial_loop(tmp_path, monkeypatch):
+    """save_data_to_hdf5(workers=N) must write exactly the reference's per-record pickle stream."""
+    import pickle
+    from zsaac_b200 import related_pipeline as rp
+    monkeypatch.setattr(rp, "WRITER_BATCH", 37)                  # several rounds + a ragged tail
+    g = torch.Generator().manual_seed(3)
+    items = [{"caption": f"caption {i}", "text_id": i, "text_embedding": torch.randn(1, 64, generator=g),
+              "related_embeddings": torch.randn(5, 64, generator=g)} for i in range(150)]
+    serial, par = tmp_path / "serial.pkl", tmp_path / "parallel.pkl"
+    rp.save_data_to_hdf5(iter(items), str(serial), len(items))
+    rp.save_data_to_hdf5(iter(items), str(par), len(items), workers=4)
+    assert serial.read_bytes() == par.read_bytes()
+    rp.save_data_to_hdf5(iter(items[:3]), str(par), 3, workers=2)            # append mode is kept
+    back = []
+    with open(par, "rb") as f:
+        while True:
+            try:
+                back.append(pickle.load(f))
+            except EOFError:
+                break
+    assert len(back) == 153 and torch.equal(back[-1]["related_embeddings"], items[2]["related_embeddings"])
+    assert not list(tmp_path.glob("*.part*"))

@@ -44,7 +44,7 @@ normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_
     return;
   }
   const InT* src = in + row * d;
-  float scale = 1.0f;
+  float denom = 1.0f;   // F.normalize divides by max(||x||, eps); x / 1 is exact when not normalising
   if (normalize) {
     float ss = 0.0f;
     for (int c = lane * 4; c < d; c += 128) {
@@ -61,7 +61,7 @@ normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_
       ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
     }
     ss = warp_sum(ss);
-    scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    denom = fmaxf(sqrtf(ss), 1e-12f);
   }
   for (int c = lane * 4; c < d; c += 128) {
     float x0, x1, x2, x3;
@@ -75,10 +75,10 @@ normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_
       x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
     }
     if constexpr (sizeof(OutT) == 4) {
-      *reinterpret_cast<float4*>(dst + c) = make_float4(x0 * scale, x1 * scale, x2 * scale, x3 * scale);
+      *reinterpret_cast<float4*>(dst + c) = make_float4(x0 / denom, x1 / denom, x2 / denom, x3 / denom);
     } else {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 * scale, x1 * scale);
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 * scale, x3 * scale);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 / denom, x1 / denom);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 / denom, x3 / denom);
       uint2 packed;
       packed.x = *reinterpret_cast<const uint32_t*>(&lo);
       packed.y = *reinterpret_cast<const uint32_t*>(&hi);

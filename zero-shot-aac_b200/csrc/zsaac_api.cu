@@ -245,7 +245,11 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
                    cudaStream_t st) {
   auto kern = zs::zs_simtopk_kernel<KCAP, CG, MODE>;
   const int smem = zs::smem_bytes<CG>();
-  ZS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool smem_opt_in[64] = {};   // per instantiation and device: opt in to > 48 KiB once
+  if (ctx->device >= 64 || !smem_opt_in[ctx->device]) {
+    ZS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (ctx->device < 64) smem_opt_in[ctx->device] = true;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));
   cfg.blockDim = dim3(zs::NUM_THREADS);

@@ -20,11 +20,13 @@ def main(argv=None):
     parser.add_argument('--input_path', type=str, help="input path files")
     parser.add_argument('--output_path', type=str, help="output path files")
     parser.add_argument('--topnumber', type=int, default=5)
+    # extension (not in the reference): pickle the output records in N forked processes
+    parser.add_argument('--writer_procs', type=int, default=None)
     args = parser.parse_args(argv)
     valid_text_embs, all_data = load_data(args.input_path)
     processed_data_gen = process_data(valid_text_embs, all_data, args.topnumber)
     total_items = len(all_data)
-    save_data_to_hdf5(processed_data_gen, args.output_path, total_items)
+    save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs)
 
 
 if __name__ == '__main__':

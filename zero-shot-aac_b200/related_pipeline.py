@@ -79,8 +79,8 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
     Reference: embeddings_related_generator.py:19-28.  valid_text_embs is the fp32 bank returned
     by load_data (CUDA).  For each item the query is F.normalize(item['text_embedding']) (:21),
     ranked by cosine similarity against the bank (:22); the k rows are gathered from
-    valid_text_embs itself (:23), so they are bit-identical to the reference's whenever the chosen
-    index is.  item['text_embedding'] is moved to the CPU (:25).  Like the reference there is no
+    valid_text_embs itself (:23): exact copies of the caller's bank rows, whatever precision the
+    search ran in.  item['text_embedding'] is moved to the CPU (:25).  Like the reference there is no
     self-exclusion unless exclude_self=True (opt-in; assumes item i is bank row i).
     """
     _require_cuda()
@@ -122,9 +122,71 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
         yield from flush(batch, base)
 
 
-def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, total_items: int) -> None:
+# records pickled per parallel round of the optional multi-process writer
+WRITER_BATCH = 8192
+_WRITER_ITEMS: List[dict] = []      # read by forked writer processes (copy-on-write, never sent)
+
+
+def _pickle_slice(args) -> str:
+    """Worker: pickle items[lo:hi] of the inherited batch into a part file; returns its path."""
+    lo, hi, part_path = args
+    with open(part_path, "wb") as f:
+        for item in _WRITER_ITEMS[lo:hi]:
+            pickle.dump(item, f)
+    return part_path
+
+
+def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str) -> None:
+    """Pickle `items` in `workers` forked processes (pickling tensors is GIL-bound Python, ~80 us
+    per record) and append the parts to `file` in order.  The bytes are exactly what the serial
+    loop would have written."""
+    import multiprocessing as mp
+    import os
+    import shutil
+    global _WRITER_ITEMS
+    _WRITER_ITEMS = items
+    n = len(items)
+    per = -(-n // workers)
+    jobs = [(lo, min(lo + per, n), f"{tmp_prefix}.part{j}") for j, lo in enumerate(range(0, n, per))]
+    try:
+        # fork: children see the batch through copy-on-write memory; they only touch CPU tensors
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            parts = pool.map(_pickle_slice, jobs)
+        for part in parts:
+            with open(part, "rb") as src:
+                shutil.copyfileobj(src, file, length=16 << 20)
+    finally:
+        _WRITER_ITEMS = []
+        for _, _, part in jobs:
+            if os.path.exists(part):
+                os.remove(part)
+
+
+def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, total_items: int,
+                      *, workers: int = None) -> None:
     """Append one pickle per record to output_path (reference :30-34; the name is historical —
-    the format is a pickle stream, read back by dataset/dataset.py:64-78)."""
+    the format is a pickle stream, read back by dataset/dataset.py:64-78).
+
+    workers (default: env ZSAAC_WRITER_PROCS, else 0): 0 reproduces the reference's serial loop;
+    N > 0 pickles batches of records in N forked processes — same bytes, same order — because
+    once the search takes milliseconds the per-record pickling dominates the script."""
+    import os
+    if workers is None:
+        workers = int(os.environ.get("ZSAAC_WRITER_PROCS", "0"))
     with open(output_path, "ab") as file:
-        for i, item in enumerate(tqdm(processed_data_gen, total=total_items)):
-            pickle.dump(item, file)
+        if workers <= 0:
+            for i, item in enumerate(tqdm(processed_data_gen, total=total_items)):
+                pickle.dump(item, file)
+            return
+        batch: List[dict] = []
+        progress = tqdm(total=total_items)
+        for item in processed_data_gen:
+            batch.append(item)
+            if len(batch) == WRITER_BATCH:
+                _write_batch_parallel(batch, file, workers, output_path)
+                progress.update(len(batch))
+                batch = []
+        if batch:
+            _write_batch_parallel(batch, file, workers, output_path)
+            progress.update(len(batch))
+        progress.close()
