@@ -115,6 +115,14 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
                   const int64_t* target_index, int n_targets, int64_t index_offset,
                   float* out_target_scores, int64_t* out_ranks, void* stream);
 
+/* Softmax-weighted projection onto the memory bank (replaces map2memory, reference
+ * predict_prompt.py:23-29: sim = q @ B.T; p = softmax(100 * sim); out = p @ B; out /= ||out||).
+ *   queries [Q, d] fp32, bank [n_rows, d] fp32 (the caller's text_features tensor, read in place:
+ *   no bank upload needed), out [Q, d] fp32.  d a multiple of 4, <= 1024.  One streaming pass
+ *   over the bank per group of 4 queries (the reference calls it with one audio embedding). */
+int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, float temperature, float* out, void* stream);
+
 /* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
  * bank chunks) under the total order (score desc, index asc).
  *   scores  list s of query q starts at scores  + s*score_stride + q*k   (float elements)

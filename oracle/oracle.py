@@ -265,3 +265,34 @@ def t2a(audio_embs, cap_embs):
             top1[5 * index + i] = inds[0]
     ap10_sum = float(np.sum(1 / (ranks[np.where(ranks < 10)[0]] + 1)))
     return _metric_summary(ranks, ap10_sum), ranks, top1
+
+
+# ------------------------------------------------------------------------------------------------
+# predict_prompt.py:23-29 (defined in the reference, its call at :134 is commented out)
+def map2memory(audio_embed: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
+    audio_embed = audio_embed.detach().cpu().float()
+    text_features = text_features.detach().cpu()
+    sim = audio_embed @ text_features.T.float()                                          # :25
+    sim = (sim * 100).softmax(dim=-1)                                                    # :26
+    prefix_embedding = sim @ text_features.float()                                       # :27
+    prefix_embedding = prefix_embedding / prefix_embedding.norm(dim=-1, keepdim=True)    # :28
+    return prefix_embedding
+
+
+# predict_prompt.py:30-56
+def construct_support_memory(paths) -> torch.Tensor:
+    import pickle
+    all_data = []
+    for dp in paths:
+        with open(dp, "rb") as f:
+            while True:
+                try:
+                    item = pickle.load(f)
+                    if type(item) is list:
+                        all_data = all_data + item
+                    elif 8 <= len(item["caption"].split()) <= 20:
+                        all_data.append(item)
+                except EOFError:
+                    break
+    text_features = torch.cat([item["text_embedding"] for item in all_data], dim=0)
+    return text_features / text_features.norm(dim=-1, keepdim=True).float()

@@ -206,7 +206,65 @@ def run_retrieval_case(name, case):
     print(f"{name}: a2t {np.round(a[:7], 2)} t2a {np.round(t[:7], 2)}")
 
 
+MEMORY_CASES = {
+    "map2memory_q1": dict(seed=4001, q=1, n=700, spread=0.35),
+    "map2memory_q5": dict(seed=4002, q=5, n=1500, spread=0.6),
+}
+
+
+def make_memory_inputs(case):
+    """Unit-norm caption memory with a few rows close to each query, so that softmax(100 * sim)
+    is neither a one-hot nor uniform."""
+    rs = np.random.RandomState(case["seed"])
+    bank = rs.standard_normal((case["n"], D)).astype(np.float32)
+    q = rs.standard_normal((case["q"], D)).astype(np.float32)
+    for i in range(case["q"]):
+        for j in range(12):
+            bank[(37 * i + 11 * j) % case["n"]] = q[i] + case["spread"] * (1 + 0.02 * j) * rs.standard_normal(D).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return q, bank
+
+
+def load_ref_functions(rel_path, names):
+    """Execute only the named top-level functions of a reference file that cannot be imported as
+    a module (predict_prompt.py pulls gpt2_prefix_eval -> a non-existent `train` module)."""
+    import ast
+    src = open(os.path.join(REF, rel_path)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "pickle": pickle}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), rel_path, "exec"), ns)
+    return ns
+
+
+def run_memory_case(name, case):
+    ns = load_ref_functions("predict_prompt.py", {"map2memory", "construct_support_memory"})
+    q, bank = make_memory_inputs(case)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")            # torch.tensor(tensor) copy-construct warning (:24)
+        out = ns["map2memory"](torch.from_numpy(q), torch.from_numpy(bank))
+    w = (torch.from_numpy(q) @ torch.from_numpy(bank).T * 100).softmax(dim=-1)
+    # construct_support_memory on a small pickle stream (dict items filtered by caption length)
+    tmp = tempfile.mkdtemp()
+    p = os.path.join(tmp, "mem.pkl")
+    caps = ["too short", "a caption that has exactly eight words in it", " ".join(["w"] * 25),
+            "another caption with nine words in it right here now"]
+    with open(p, "wb") as f:
+        for i, c in enumerate(caps):
+            pickle.dump({"caption": c, "text_embedding": torch.from_numpy(bank[i:i + 1] * (i + 2.0))}, f)
+        pickle.dump([{"caption": "listed", "text_embedding": torch.from_numpy(bank[9:10] * 3.0)}], f)
+    mem = ns["construct_support_memory"]([p])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), out=out.numpy(),
+                        max_weight=w.max(dim=1).values.numpy(), memory=mem.numpy())
+    print(f"{name}: max softmax weight per query {np.round(w.max(dim=1).values.numpy(), 3)} memory rows {tuple(mem.shape)}")
+
+
 if __name__ == "__main__":
+    for n, c in MEMORY_CASES.items():
+        run_memory_case(n, c)
     for n, c in RETRIEVAL_CASES.items():
         run_retrieval_case(n, c)
     for n, c in CASES.items():

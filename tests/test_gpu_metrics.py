@@ -103,3 +103,42 @@ def test_a2t_t2a_match_reference_golden(name):
             # ties go to the ground truth here, to an arbitrary item in the reference: the
             # metrics can only be equal or better
             assert plain[0] >= g[key + "_metrics"][0] - 1e-9 and plain[5] <= g[key + "_metrics"][5] + 1e-9
+
+
+# ------------------------------------------------------------------------------ map2memory (row a8)
+@pytest.mark.parametrize("name", list(recipes.MEMORY_CASES))
+def test_map2memory_matches_reference_golden(name, tmp_path):
+    import pickle
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.predict_prompt import construct_support_memory, map2memory
+    q, bank = recipes.make_memory_inputs(recipes.MEMORY_CASES[name])
+    g = helpers.golden(name)
+    for dev in ("cpu", "cuda"):
+        out = map2memory(torch.from_numpy(q).to(dev), torch.from_numpy(bank).to(dev))
+        assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == q.shape
+        # fp32 everywhere; the fast exp and a different summation order leave ~1e-6
+        assert (out.cpu() - torch.from_numpy(g["out"])).abs().max().item() < 2e-5
+        assert (out.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    p = tmp_path / "mem.pkl"
+    caps = ["too short", "a caption that has exactly eight words in it", " ".join(["w"] * 25),
+            "another caption with nine words in it right here now"]
+    with open(p, "wb") as f:
+        for i, c in enumerate(caps):
+            pickle.dump({"caption": c, "text_embedding": torch.from_numpy(bank[i:i + 1] * (i + 2.0))}, f)
+        pickle.dump([{"caption": "listed", "text_embedding": torch.from_numpy(bank[9:10] * 3.0)}], f)
+    mem = construct_support_memory([str(p)])
+    assert mem.is_cuda and (mem.cpu() - torch.from_numpy(g["memory"])).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("Q,N,d", [(1, 400_000, 1024), (3, 50_001, 1024), (9, 1000, 512), (2, 7, 64)])
+def test_map2memory_against_oracle_at_scale(Q, N, d):
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.predict_prompt import map2memory
+    gen = torch.Generator(device="cuda").manual_seed(Q + N)
+    bank = torch.nn.functional.normalize(torch.randn(N, d, device="cuda", generator=gen), dim=-1)
+    q = torch.nn.functional.normalize(torch.randn(Q, d, device="cuda", generator=gen), dim=-1)
+    q[0] = torch.nn.functional.normalize(bank[N // 2] + 0.02 * q[0], dim=-1)     # one peaked query
+    out = map2memory(q, bank)
+    torch.cuda.synchronize()
+    want = oracle.map2memory(q.cpu(), bank.cpu())
+    assert (out.cpu() - want).abs().max().item() < 5e-5

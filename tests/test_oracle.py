@@ -148,3 +148,23 @@ def test_retrieval_metrics_match_reference_golden(name):
     np.testing.assert_array_equal(ranks, g["t2a_ranks"])
     np.testing.assert_array_equal(top1, g["t2a_top1"])
     assert 0 < g["a2t_metrics"][0] < 100 and 0 < g["t2a_metrics"][0] < 100   # a non-trivial fixture
+
+
+@pytest.mark.parametrize("name", list(recipes.MEMORY_CASES))
+def test_map2memory_matches_reference_golden(name, tmp_path):
+    """map2memory / construct_support_memory restated (oracle) vs the reference's own functions."""
+    import pickle
+    q, bank = recipes.make_memory_inputs(recipes.MEMORY_CASES[name])
+    g = helpers.golden(name)
+    out = oracle.map2memory(torch.from_numpy(q), torch.from_numpy(bank))
+    np.testing.assert_allclose(out.numpy(), g["out"], atol=1e-6)
+    assert (g["max_weight"] < 0.9).all()         # the fixture is not a one-hot softmax
+    p = tmp_path / "mem.pkl"
+    caps = ["too short", "a caption that has exactly eight words in it", " ".join(["w"] * 25),
+            "another caption with nine words in it right here now"]
+    with open(p, "wb") as f:
+        for i, c in enumerate(caps):
+            pickle.dump({"caption": c, "text_embedding": torch.from_numpy(bank[i:i + 1] * (i + 2.0))}, f)
+        pickle.dump([{"caption": "listed", "text_embedding": torch.from_numpy(bank[9:10] * 3.0)}], f)
+    mem = oracle.construct_support_memory([str(p)])
+    np.testing.assert_allclose(mem.numpy(), g["memory"], atol=1e-7)

@@ -17,6 +17,7 @@
 
 #include "../../include/zsaac.h"
 #include "aux_kernels.cuh"
+#include "memproj_kernel.cuh"
 #include "simtopk_kernel.cuh"
 
 namespace {
@@ -80,6 +81,8 @@ struct zs_ctx {
   int* tgt_cols = nullptr;
   int* part_counts = nullptr;         // [chunks * EPI_HALVES, Q, T]
   int64_t tgt_elems = 0, count_elems = 0;
+  float* memproj_partials = nullptr;  // zs_memory_project: [warps, 4, d + 4]
+  int64_t memproj_elems = 0;
   unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
   int64_t sync_cnt_elems = 0;
 
@@ -369,6 +372,7 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->part_idx);
   cudaFree(ctx->err_flag);
   cudaFree(ctx->sync_cnt);
+  cudaFree(ctx->memproj_partials);
   cudaFree(ctx->tgt_scores);
   cudaFree(ctx->tgt_cols);
   cudaFree(ctx->part_counts);
@@ -621,6 +625,50 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
   if (out_target_scores)
     ZS_CUDA(cudaMemcpyAsync(out_target_scores, ctx->tgt_scores, static_cast<size_t>(n_pairs) * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
+  return ZS_OK;
+}
+
+int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, float temperature, float* out, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_memory_project: ctx is null");
+  if (Q < 0 || n_rows < 1) return fail(ZS_ERR_INVALID, "zs_memory_project: Q=%lld n_rows=%lld",
+                                       (long long)Q, (long long)n_rows);
+  if (d < 4 || d % 4 != 0 || d > zs::MEMPROJ_MAX_D)
+    return fail(ZS_ERR_INVALID, "zs_memory_project: d=%d must be a multiple of 4, at most %d", d,
+                zs::MEMPROJ_MAX_D);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !bank || !out) return fail(ZS_ERR_INVALID, "zs_memory_project: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int QB = 4;                                    // queries per pass over the bank
+  const int blocks = ctx->sm_count * 2;
+  const int64_t total_warps = static_cast<int64_t>(blocks) * (zs::MEMPROJ_THREADS / 32);
+  const int64_t need = total_warps * QB * zs::memproj_partial_stride(d);
+  if (need > ctx->memproj_elems) {
+    if (ctx->memproj_partials) { ZS_CUDA(cudaFree(ctx->memproj_partials)); ctx->memproj_partials = nullptr; }
+    ctx->memproj_elems = 0;
+    ZS_CUDA(cudaMalloc(&ctx->memproj_partials, static_cast<size_t>(need) * sizeof(float)));
+    ctx->memproj_elems = need;
+  }
+  for (int64_t q0 = 0; q0 < Q; q0 += QB) {
+    const int nq = static_cast<int>(std::min<int64_t>(QB, Q - q0));
+    const float* qptr = queries + q0 * d;
+    // 1 or 2 queries use the narrower instantiations (fewer accumulator registers, more warps in flight)
+    if (nq == 1)
+      zs::memproj_stream_kernel<1><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
+                                                                          temperature, ctx->memproj_partials);
+    else if (nq == 2)
+      zs::memproj_stream_kernel<2><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
+                                                                          temperature, ctx->memproj_partials);
+    else
+      zs::memproj_stream_kernel<4><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
+                                                                          temperature, ctx->memproj_partials);
+    ZS_CUDA(cudaGetLastError());
+    const int qb = nq == 1 ? 1 : (nq == 2 ? 2 : 4);
+    zs::memproj_combine_kernel<<<nq, 256, 0, st>>>(ctx->memproj_partials, total_warps, qb, d, out + q0 * d);
+    ZS_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+  }
   return ZS_OK;
 }
 
