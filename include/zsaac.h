@@ -119,7 +119,7 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
  * predict_prompt.py:23-29: sim = q @ B.T; p = softmax(100 * sim); out = p @ B; out /= ||out||).
  *   queries [Q, d] fp32, bank [n_rows, d] fp32 (the caller's text_features tensor, read in place:
  *   no bank upload needed), out [Q, d] fp32.  d a multiple of 4, <= 1024.  One streaming pass
- *   over the bank per group of 4 queries (the reference calls it with one audio embedding). */
+ *   over the bank per group of 2 queries (the reference calls it with one audio embedding). */
 int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
                       int d, float temperature, float* out, void* stream);
 

@@ -11,8 +11,9 @@
 // memproj_stream_kernel: one warp owns rows j = warp, warp + W, ...; per row it computes the QB
 // similarities (warp reduction) and keeps, per query, a running maximum m, normaliser Z and
 // weighted sum acc[d] (online softmax: acc is only rescaled when the maximum moves).  Every
-// warp writes its partial (m, Z, acc).  memproj_combine_kernel folds the W partials per query
-// with the usual exp(m_w - M) rescale, divides by Z and L2-normalises.
+// block folds its 8 warps and writes one partial (m, Z, acc).  memproj_combine_kernel folds the
+// per-block partials per query with the usual exp(m_b - M) rescale and divides by Z;
+// memproj_finalize_kernel L2-normalises.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(MEMPROJ_THREADS)
 memproj_stream_kernel(const float* __restrict__ queries,   // [QB_valid, d]
                       const float* __restrict__ bank,      // [n_rows, d] fp32
                       int64_t n_rows, int d, int n_valid_queries, float temperature,
-                      float* __restrict__ partials) {      // [total_warps, QB, d + 4]
+                      float* __restrict__ partials) {      // [gridDim.x, QB, d + 4]
   __shared__ float4 q_s[QB][MEMPROJ_MAX_D / 4];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -112,33 +113,67 @@ memproj_stream_kernel(const float* __restrict__ queries,   // [QB_valid, d]
     row = next;
   }
 
+  // fold the 8 warps of the block into one partial per query (one after the other through smem:
+  // runs once per launch) so that the combine step reads gridDim.x partials, not 8x as many
+  __shared__ float m_s[MEMPROJ_THREADS / 32];
+  __shared__ __align__(16) float acc_s[MEMPROJ_MAX_D];
   const int64_t stride = memproj_partial_stride(d);
 #pragma unroll
   for (int q = 0; q < QB; ++q) {
-    float* dst = partials + (warp * QB + q) * stride;
-    if (lane == 0) { dst[0] = m[q]; dst[1] = z[q]; }
-    float4* dv = reinterpret_cast<float4*>(dst + 4);
+    if (lane == 0) m_s[warp_in_block] = m[q];
+    __syncthreads();
+    float mb = -CUDART_INF_F;
 #pragma unroll
-    for (int v = 0; v < MEMPROJ_VEC; ++v) {
-      const int c = lane + 32 * v;
-      if (c < nvec) dv[c] = acc[q][v];
+    for (int w = 0; w < MEMPROJ_THREADS / 32; ++w) mb = fmaxf(mb, m_s[w]);
+    const float r = (m[q] == -CUDART_INF_F) ? 0.f : __expf(m[q] - mb);    // warps without rows add 0
+    float zb = z[q] * r;
+    for (int w = 0; w < MEMPROJ_THREADS / 32; ++w) {
+      if (warp_in_block == w) {
+#pragma unroll
+        for (int v = 0; v < MEMPROJ_VEC; ++v) {
+          const int c = lane + 32 * v;
+          if (c < nvec) {
+            float4* a = reinterpret_cast<float4*>(acc_s) + c;
+            float4 cur4 = (w == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : *a;
+            cur4.x = fmaf(r, acc[q][v].x, cur4.x); cur4.y = fmaf(r, acc[q][v].y, cur4.y);
+            cur4.z = fmaf(r, acc[q][v].z, cur4.z); cur4.w = fmaf(r, acc[q][v].w, cur4.w);
+            *a = cur4;
+          }
+        }
+      }
+      __syncthreads();
     }
+    // Z of the block: fixed-order sum over the warps
+    __shared__ float z_s[MEMPROJ_THREADS / 32];
+    if (lane == 0) z_s[warp_in_block] = zb;
+    __syncthreads();
+    float* dst = partials + (static_cast<int64_t>(blockIdx.x) * QB + q) * stride;
+    if (threadIdx.x == 0) {
+      float zt = 0.f;
+      for (int w = 0; w < MEMPROJ_THREADS / 32; ++w) zt += z_s[w];
+      dst[0] = mb;
+      dst[1] = zt;
+    }
+    for (int c = threadIdx.x; c < nvec; c += MEMPROJ_THREADS)
+      reinterpret_cast<float4*>(dst + 4)[c] = reinterpret_cast<const float4*>(acc_s)[c];
+    __syncthreads();
   }
 }
 
-// One block per query: fold the per-warp partials, divide by Z, L2-normalise (out /= ||out||,
-// predict_prompt.py:28 — no epsilon there either; an all-zero result stays zero here).
+// Combine the per-block partials of one query: grid (d / 64 column groups, queries), 256 threads
+// = 64 columns x 4 slices of the partial list.  Writes the un-normalised softmax-weighted sum.
+constexpr int MEMPROJ_COMBINE_COLS = 64;
 __global__ void __launch_bounds__(256)
-memproj_combine_kernel(const float* __restrict__ partials, int64_t total_warps, int qb, int d,
+memproj_combine_kernel(const float* __restrict__ partials, int n_partials, int qb, int d,
                        float* __restrict__ out /* [qb_valid, d] */) {
-  const int q = blockIdx.x;
+  const int q = blockIdx.y;
   const int64_t stride = memproj_partial_stride(d);
   __shared__ float red[256];
-  __shared__ float bcast;
+  __shared__ float colsum[4][MEMPROJ_COMBINE_COLS];
 
   float mx = -CUDART_INF_F;
-  for (int64_t w = threadIdx.x; w < total_warps; w += blockDim.x)
-    mx = fmaxf(mx, partials[(w * qb + q) * stride]);
+  for (int b = threadIdx.x; b < n_partials; b += blockDim.x)
+    mx = fmaxf(mx, partials[(static_cast<int64_t>(b) * qb + q) * stride]);
   red[threadIdx.x] = mx;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -147,11 +182,10 @@ memproj_combine_kernel(const float* __restrict__ partials, int64_t total_warps, 
   }
   const float M = red[0];
   __syncthreads();
-
   float zsum = 0.f;
-  for (int64_t w = threadIdx.x; w < total_warps; w += blockDim.x) {
-    const float* p = partials + (w * qb + q) * stride;
-    zsum += __expf(p[0] - M) * p[1];
+  for (int b = threadIdx.x; b < n_partials; b += blockDim.x) {
+    const float* p = partials + (static_cast<int64_t>(b) * qb + q) * stride;
+    zsum += (p[0] == -CUDART_INF_F) ? 0.f : __expf(p[0] - M) * p[1];
   }
   red[threadIdx.x] = zsum;
   __syncthreads();
@@ -160,19 +194,34 @@ memproj_combine_kernel(const float* __restrict__ partials, int64_t total_warps, 
     __syncthreads();
   }
   const float Z = red[0];
-  __syncthreads();
 
-  // each thread owns columns c = threadIdx.x, + 256, ...; fixed summation order over warps
+  const int col = blockIdx.x * MEMPROJ_COMBINE_COLS + (threadIdx.x & (MEMPROJ_COMBINE_COLS - 1));
+  const int slice = threadIdx.x / MEMPROJ_COMBINE_COLS;          // 0..3
+  float a = 0.f;
+  if (col < d) {
+    for (int b = slice; b < n_partials; b += 4) {
+      const float* p = partials + (static_cast<int64_t>(b) * qb + q) * stride;
+      const float e = (p[0] == -CUDART_INF_F) ? 0.f : __expf(p[0] - M);
+      a = fmaf(e, p[4 + col], a);
+    }
+  }
+  colsum[slice][threadIdx.x & (MEMPROJ_COMBINE_COLS - 1)] = a;
+  __syncthreads();
+  if (slice == 0 && col < d) {
+    const int c = threadIdx.x;
+    out[static_cast<int64_t>(q) * d + col] = (colsum[0][c] + colsum[1][c] + colsum[2][c] + colsum[3][c]) / Z;
+  }
+}
+
+// out[q] /= ||out[q]||  (predict_prompt.py:28 — no epsilon there either; an all-zero row stays 0)
+__global__ void __launch_bounds__(256)
+memproj_finalize_kernel(float* __restrict__ out, int d) {
+  const int q = blockIdx.x;
+  __shared__ float red[256];
   float ss = 0.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a = 0.f;
-    for (int64_t w = 0; w < total_warps; ++w) {
-      const float* p = partials + (w * qb + q) * stride;
-      a = fmaf(__expf(p[0] - M), p[4 + c], a);
-    }
-    a /= Z;
-    out[static_cast<int64_t>(q) * d + c] = a;
-    ss = fmaf(a, a, ss);
+    const float v = out[static_cast<int64_t>(q) * d + c];
+    ss = fmaf(v, v, ss);
   }
   red[threadIdx.x] = ss;
   __syncthreads();
@@ -180,9 +229,7 @@ memproj_combine_kernel(const float* __restrict__ partials, int64_t total_warps, 
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) bcast = sqrtf(red[0]);
-  __syncthreads();
-  const float norm = bcast;
+  const float norm = sqrtf(red[0]);
   if (norm > 0.f)
     for (int c = threadIdx.x; c < d; c += blockDim.x) out[static_cast<int64_t>(q) * d + c] /= norm;
 }

@@ -81,7 +81,7 @@ struct zs_ctx {
   int* tgt_cols = nullptr;
   int* part_counts = nullptr;         // [chunks * EPI_HALVES, Q, T]
   int64_t tgt_elems = 0, count_elems = 0;
-  float* memproj_partials = nullptr;  // zs_memory_project: [warps, 4, d + 4]
+  float* memproj_partials = nullptr;  // zs_memory_project: [blocks, 2, d + 4]
   int64_t memproj_elems = 0;
   unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
   int64_t sync_cnt_elems = 0;
@@ -640,10 +640,11 @@ int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float*
   if (!queries || !bank || !out) return fail(ZS_ERR_INVALID, "zs_memory_project: null pointer");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  constexpr int QB = 4;                                    // queries per pass over the bank
+  // queries per pass over the bank: 2 (157 registers, 2 blocks per SM) streams at HBM speed;
+  // the 4-query instantiation needs 225 registers and was measured slower per query
+  constexpr int QB = 2;
   const int blocks = ctx->sm_count * 2;
-  const int64_t total_warps = static_cast<int64_t>(blocks) * (zs::MEMPROJ_THREADS / 32);
-  const int64_t need = total_warps * QB * zs::memproj_partial_stride(d);
+  const int64_t need = static_cast<int64_t>(blocks) * QB * zs::memproj_partial_stride(d);
   if (need > ctx->memproj_elems) {
     if (ctx->memproj_partials) { ZS_CUDA(cudaFree(ctx->memproj_partials)); ctx->memproj_partials = nullptr; }
     ctx->memproj_elems = 0;
@@ -657,17 +658,16 @@ int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float*
     if (nq == 1)
       zs::memproj_stream_kernel<1><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
                                                                           temperature, ctx->memproj_partials);
-    else if (nq == 2)
+    else
       zs::memproj_stream_kernel<2><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
                                                                           temperature, ctx->memproj_partials);
-    else
-      zs::memproj_stream_kernel<4><<<blocks, zs::MEMPROJ_THREADS, 0, st>>>(qptr, bank, n_rows, d, nq,
-                                                                          temperature, ctx->memproj_partials);
     ZS_CUDA(cudaGetLastError());
-    const int qb = nq == 1 ? 1 : (nq == 2 ? 2 : 4);
-    zs::memproj_combine_kernel<<<nq, 256, 0, st>>>(ctx->memproj_partials, total_warps, qb, d, out + q0 * d);
+    const int qb = nq;
+    const dim3 cgrid((d + zs::MEMPROJ_COMBINE_COLS - 1) / zs::MEMPROJ_COMBINE_COLS, nq);
+    zs::memproj_combine_kernel<<<cgrid, 256, 0, st>>>(ctx->memproj_partials, blocks, qb, d, out + q0 * d);
+    zs::memproj_finalize_kernel<<<nq, 256, 0, st>>>(out + q0 * d, d);
     ZS_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 3;
   }
   return ZS_OK;
 }
