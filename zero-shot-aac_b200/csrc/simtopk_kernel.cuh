@@ -17,8 +17,9 @@
 //                epilogue of bank tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
 // A work unit is (query tile, bank chunk); units are walked persistently with a static stride.
 // Every unit writes, per row and column half, its k best (score, column) pairs;
-// merge_lists_kernel reduces the 2 x chunks lists.  CG == 2 pairs two CTAs of a cluster on a 256-row query tile (cta_group::2): each CTA
-// loads its own 128 query rows and half of the bank tile.
+// merge_lists_kernel reduces the 2 x chunks lists.  CG == 2 pairs two CTAs of a cluster on a
+// 256-row query tile (cta_group::2): each CTA loads its own 128 query rows and half of the bank
+// tile, the leader issues the MMAs for both.
 #pragma once
 
 #include <math_constants.h>
@@ -35,7 +36,6 @@ constexpr int UMMA_K = 16;
 // 32 KiB bank) and 32 KiB per CTA of a pair (16 + 16), so a pair can run 6 stages deep
 template <int CG>
 constexpr int num_stages() { return CG == 2 ? 6 : 4; }
-constexpr int MAX_STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512: the whole tensor memory of the SM
 constexpr int EPI_WARP0 = 4;
