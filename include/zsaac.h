@@ -147,6 +147,12 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t zs_launch_count(const zs_ctx* ctx);
 
+/* Role code written by a fused-kernel pipeline wait that timed out (the kernel then traps, which
+ * poisons the CUDA context — ZS_ERR_KERNEL territory): 0 none, 101 TMA producer, 102 MMA issuer
+ * waiting for operands, 103 MMA issuer waiting for an accumulator, 104 epilogue.  The code lives
+ * in mapped host memory, so it stays readable after the trap. */
+int zs_kernel_error(const zs_ctx* ctx);
+
 /* Per-launch device timing of the fused similarity+top-k kernel.  With enable != 0 every
  * zs_search brackets that kernel with CUDA events on the caller's stream (a ring of
  * ZS_PROFILE_RING launches; enabling resets the ring).  zs_profile_read synchronises on the

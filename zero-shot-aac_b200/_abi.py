@@ -50,6 +50,7 @@ SIGNATURES = {
     "zs_plan": (_int, [_c_ctx, _i64, _int, ctypes.POINTER(_int), ctypes.POINTER(_int),
                        ctypes.POINTER(_int)]),
     "zs_launch_count": (_i64, [_c_ctx]),
+    "zs_kernel_error": (_int, [_c_ctx]),
     "zs_profile_enable": (_int, [_c_ctx, _int]),
     "zs_profile_read": (_int, [_c_ctx, ctypes.POINTER(ctypes.c_float), _int, ctypes.POINTER(_int)]),
     "zs_debug_scores": (_int, [_c_ctx, _ptr, _i64, _int, _int, _ptr, _ptr]),

@@ -98,7 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > ZS_WAIT_TIMEOUT_CYCLES) {
-      if (err) atomicExch(err, code);
+      if (err) *reinterpret_cast<volatile int*>(err) = code;   // mapped host memory
       __threadfence_system();
       __trap();
     }

@@ -76,7 +76,8 @@ struct zs_ctx {
   float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
   int64_t part_elems = 0;
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;            // device alias of err_host
+  int* err_host = nullptr;            // pinned + mapped: readable after a kernel trap
   float* tgt_scores = nullptr;        // rank mode: [Q, T]
   int* tgt_cols = nullptr;
   int* part_counts = nullptr;         // [chunks * EPI_HALVES, Q, T]
@@ -353,11 +354,17 @@ int zs_create(zs_ctx** out, int device) {
   if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group_override = cg[0] - '0';
   const char* pdl = getenv("ZSAAC_PDL");
   if (pdl && pdl[0] == '0') ctx->pdl_enabled = false;
-  e = cudaMalloc(&ctx->err_flag, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(ctx->err_flag, 0, sizeof(int));
+  // the role code of a timed-out pipeline wait goes to mapped host memory, so that it can still
+  // be read after the trap has poisoned the CUDA context
+  e = cudaHostAlloc(&ctx->err_host, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *ctx->err_host = 0;
+    e = cudaHostGetDevicePointer(&ctx->err_flag, ctx->err_host, 0);
+  }
   if (e != cudaSuccess) {
+    if (ctx->err_host) cudaFreeHost(ctx->err_host);
     delete ctx;
-    return fail(ZS_ERR_CUDA, "zs_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    return fail(ZS_ERR_CUDA, "zs_create: mapped host allocation failed: %s", cudaGetErrorString(e));
   }
   *out = ctx;
   return ZS_OK;
@@ -370,7 +377,7 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->q_ws);
   cudaFree(ctx->part_scores);
   cudaFree(ctx->part_idx);
-  cudaFree(ctx->err_flag);
+  cudaFreeHost(ctx->err_host);
   cudaFree(ctx->sync_cnt);
   cudaFree(ctx->memproj_partials);
   cudaFree(ctx->tgt_scores);
@@ -454,6 +461,8 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 }
 
 int64_t zs_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zs_kernel_error(const zs_ctx* ctx) { return (ctx && ctx->err_host) ? *ctx->err_host : 0; }
 
 int zs_profile_enable(zs_ctx* ctx, int enable) {
   if (!ctx) return fail(ZS_ERR_INVALID, "zs_profile_enable: ctx is null");

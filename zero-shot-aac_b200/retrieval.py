@@ -258,6 +258,11 @@ class RelatedBank:
         return [float(buf[j]) for j in range(n.value)]
 
     @property
+    def kernel_error(self) -> int:
+        """Role code of a timed-out pipeline wait (0 = none); readable even after a kernel trap."""
+        return int(self._lib.zs_kernel_error(self._ctx))
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.zs_launch_count(self._ctx))
 
