@@ -178,6 +178,9 @@ def run_reference(args):
     if rank != 0:
         return 0                                                  # rank 0 alone runs this arm
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; this arm is the CPU reference
+    # and is entitled to every host thread
+    torch.set_num_threads(os.cpu_count() or 1)
     name = args.workload
     Q, N, k, excl, _, _ = WORKLOADS[name]
     ref = CpuReference(torch, name)
@@ -349,6 +352,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
         ref = CpuReference(torch, name)
         cpu_baseline = ref.baseline(min(ref.one_pass() for _ in range(2)))
 
