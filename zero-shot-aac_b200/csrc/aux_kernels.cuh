@@ -123,18 +123,26 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
   if (q >= Q) return;
 
   const long long SENT = 0x7fffffffffffffffll;
+  // per owned list: position of the current head, the head itself and the element after it (the
+  // successor is fetched one round ahead, so the merge never waits on a dependent global load)
   int head[LPL];
-  float hs[LPL];
-  long long hi[LPL];
+  float hs[LPL], ns[LPL];
+  long long hi[LPL], ni[LPL];
 #pragma unroll
   for (int l = 0; l < LPL; ++l) {
     const int list = lane + 32 * l;
     head[l] = 0;
-    hs[l] = -CUDART_INF_F;
-    hi[l] = SENT;
+    hs[l] = ns[l] = -CUDART_INF_F;
+    hi[l] = ni[l] = SENT;
     if (list < S) {
-      hs[l] = scores[static_cast<int64_t>(list) * score_stride + q * k];
-      hi[l] = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k]);
+      const int64_t so = static_cast<int64_t>(list) * score_stride + q * k;
+      const int64_t io = static_cast<int64_t>(list) * index_stride + q * k;
+      hs[l] = scores[so];
+      hi[l] = widen_index(idx[io]);
+      if (k > 1) {
+        ns[l] = scores[so + 1];
+        ni[l] = widen_index(idx[io + 1]);
+      }
     } else {
       head[l] = k;  // exhausted
     }
@@ -161,15 +169,18 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
       out_scores[q * k + r] = best.s;
       out_idx[q * k + r] = (best.i == SENT) ? -1ll : best.i + idx_offset;
     }
-    // the owner of the winning list advances it
+    // the owner of the winning list advances it: the prefetched successor becomes the head and
+    // the element after that is requested
 #pragma unroll
     for (int l = 0; l < LPL; ++l) {
       if (best.src == lane * LPL + l) {
         ++head[l];
-        if (head[l] < k) {
+        hs[l] = ns[l];
+        hi[l] = ni[l];
+        if (head[l] + 1 < k) {
           const int64_t list = lane + 32 * l;
-          hs[l] = scores[list * score_stride + q * k + head[l]];
-          hi[l] = widen_index(idx[list * index_stride + q * k + head[l]]);
+          ns[l] = scores[list * score_stride + q * k + head[l] + 1];
+          ni[l] = widen_index(idx[list * index_stride + q * k + head[l] + 1]);
         }
       }
     }

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +45,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Every kernel moves rows with 8- or 16-byte vector accesses; torch allocations are 256-byte
+// aligned and row offsets are multiples of 2*d (d % 64 == 0), but a raw pointer handed in over
+// the C ABI might not be.
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct DeviceGuard {
   int prev = -1;
@@ -430,6 +436,7 @@ int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_ro
   if (in_dtype != ZS_F32 && in_dtype != ZS_BF16)
     return fail(ZS_ERR_INVALID, "zs_bank_upload: unknown dtype %d", in_dtype);
   if (n_rows == 0) return ZS_OK;
+  if (!aligned16(rows)) return fail(ZS_ERR_INVALID, "zs_bank_upload: rows must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* dst = ctx->bank + dst_row * ctx->bank_d;
@@ -511,6 +518,7 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   if (Q == 0) return ZS_OK;
   if (!queries || !out_scores || !out_indices)
     return fail(ZS_ERR_INVALID, "zs_search: null queries / output pointer");
+  if (!aligned16(queries)) return fail(ZS_ERR_INVALID, "zs_search: queries must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_workspace(ctx, Q, k);
@@ -574,6 +582,7 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
   if (Q == 0) return ZS_OK;
   if (!queries || !target_index || !out_ranks)
     return fail(ZS_ERR_INVALID, "zs_rank_count: null pointer");
+  if (!aligned16(queries)) return fail(ZS_ERR_INVALID, "zs_rank_count: queries must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_workspace(ctx, Q, 1);
@@ -647,6 +656,8 @@ int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float*
                 zs::MEMPROJ_MAX_D);
   if (Q == 0) return ZS_OK;
   if (!queries || !bank || !out) return fail(ZS_ERR_INVALID, "zs_memory_project: null pointer");
+  if (!aligned16(queries) || !aligned16(bank) || !aligned16(out))
+    return fail(ZS_ERR_INVALID, "zs_memory_project: queries, bank and out must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // queries per pass over the bank: 2 (157 registers, 2 blocks per SM) streams at HBM speed;
@@ -709,6 +720,8 @@ int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,
   if (n_idx < 0 || n_src_rows < 0) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: negative size");
   if (n_idx == 0) return ZS_OK;
   if (!src || !indices || !out) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: null pointer");
+  if (!aligned16(src) || !aligned16(out))
+    return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: src and out must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (n_idx * 32 + 255) / 256;
@@ -727,6 +740,8 @@ int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_ro
                 (long long)n_rows, d);
   if (n_rows == 0) return ZS_OK;
   if (!in || !out) return fail(ZS_ERR_INVALID, "zs_normalize_rows_f32: null pointer");
+  if (!aligned16(in) || !aligned16(out))
+    return fail(ZS_ERR_INVALID, "zs_normalize_rows_f32: in and out must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (n_rows * 32 + 255) / 256;
