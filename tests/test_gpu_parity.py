@@ -293,6 +293,46 @@ def test_wavcaps_scale_properties(zs):
     rbp.close()
 
 
+# ------------------------------------------------------------------ shared admission thresholds
+@pytest.mark.parametrize("Q,N,k,chunks", [(300, 40_000, 10, 150), (700, 60_000, 32, 200),
+                                          (129, 30_000, 5, 117), (975, 49_838, 10, 0),
+                                          (2100, 21_000, 1, 80)])
+def test_threshold_sharing_is_result_neutral(zs, cta_group, monkeypatch, Q, N, k, chunks):
+    """Units publish the k-th score of their list per query row and later units start from it
+    (SimTopkParams::row_thr).  Many forced chunks make units run in several waves, so most of them
+    are seeded by earlier ones; the merged result must be identical to the unshared run."""
+    q, b = helpers.seeded((Q, 1024), 400 + k), helpers.clustered(N, 1024, 512, 0.05, 401 + k)
+    if chunks:
+        monkeypatch.setenv("ZSAAC_CHUNKS", str(chunks))
+    monkeypatch.setenv("ZSAAC_SHARE_THR", "0")
+    s0, i0 = run_search(zs, q, b, k)
+    monkeypatch.setenv("ZSAAC_SHARE_THR", "1")
+    s1, i1 = run_search(zs, q, b, k)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    rep = oracle.check_topk(s1[:64], i1[:64], q[:64], b, k)
+    assert rep["ok"], rep
+
+
+def test_threshold_sharing_keeps_index_order_on_exact_ties(zs, cta_group, monkeypatch):
+    """Exact ties across chunk boundaries: a unit seeded with threshold t still admits scores
+    EQUAL to t (the tie-break is the index).  Identical rows -> the first k indices; an all-zero
+    query scores exactly 0.0 everywhere (pred(+0) must step below -0 as well)."""
+    monkeypatch.setenv("ZSAAC_CHUNKS", "200")
+    row = helpers.seeded((1, 1024), 411)
+    bank = row.expand(52_000, 1024).contiguous()
+    q = torch.cat([helpers.seeded((299, 1024), 412), torch.zeros(1, 1024)])
+    for k in (1, 7, 32):
+        s, i = run_search(zs, q, bank, k)
+        assert torch.equal(i, torch.arange(k).expand(300, k)), k
+        assert (s[-1] == 0).all()
+    # half the bank identical and best, placed at the END: chunks that run first publish lower
+    # thresholds, the tied block must still come out in ascending index order
+    bank2 = torch.cat([helpers.seeded((26_000, 1024), 413), row.expand(26_000, 1024)]).contiguous()
+    qq = row + 0.01 * helpers.seeded((300, 1024), 414)
+    s, i = run_search(zs, qq, bank2, 32)
+    assert torch.equal(i, (26_000 + torch.arange(32)).expand(300, 32))
+
+
 # ---------------------------------------------------------------- adversarial orderings / hypothesis
 def test_adversarially_ordered_bank(zs, cta_group):
     """Bank sorted by similarity to the queries: ascending order makes EVERY score a new maximum

@@ -16,12 +16,19 @@ dev = torch.device("cuda", 0)
 
 SHAPES = {
     # name: (Q, N, [k ...], [chunks ...]); chunks 0 = the library's own plan
-    "shard": (65536, 1_250_000, [32, 10, 1], [0, 1, 2, 4, 9, 19]),      # one rank of config 4 at 8 GPUs
-    "wavcaps": (8192, 400_000, [10, 1, 32], [0, 2, 7, 9, 19]),
-    "k32": (16384, 400_000, [32, 10, 1], [0, 4, 9, 14, 23]),
-    "audiocaps": (975, 49838, [10, 1, 32], [0, 9, 12, 24]),
-    "clotho": (1045, 19195, [5, 1], [0, 7, 14]),
+    "shard": (65536, 1_250_000, [32, 10, 1], [0, 2, 4, 9]),      # one rank of config 4 at 8 GPUs
+    "wavcaps": (8192, 400_000, [10, 1, 32], [0, 2, 9, 19]),
+    "k32": (16384, 400_000, [32, 10, 1], [0, 4, 9]),
+    "audiocaps": (975, 49838, [10, 1, 32], [0, 24]),
+    "clotho": (1045, 19195, [5, 1], [0]),
 }
+
+
+# A/B variants: ';'-separated sets of ','-separated library tuning variables, e.g.
+#   SWEEP_VARIANTS="ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0;ZSAAC_LOCKSTEP=0"
+VARIANTS = [dict(kv.split("=") for kv in v.split(",") if kv)
+            for v in os.environ.get("SWEEP_VARIANTS", "ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0").split(";")]
+TUNABLES = ("ZSAAC_SHARE_THR", "ZSAAC_LOCKSTEP")
 
 
 def time_kernel(rb, q, k, out, reps):
@@ -61,12 +68,18 @@ def main():
                     os.environ.pop("ZSAAC_CHUNKS", None)
                 rb.reserve(Q, k)
                 reps = 5 if flop > 1e14 else 20
-                med, kern = time_kernel(rb, q, k, out, reps)
-                print(json.dumps({"shape": name, "Q": Q, "N": N, "k": k, "chunks_forced": chunks,
-                                  "plan": rb.plan(Q, k), "search_ms": round(med, 4),
-                                  "kernel_ms": round(kern, 4),
-                                  "kernel_tflops": round(flop / (kern * 1e-3) / 1e12, 1)}), flush=True)
+                for var in VARIANTS:
+                    for t in TUNABLES:
+                        os.environ.pop(t, None)
+                    os.environ.update(var)
+                    med, kern = time_kernel(rb, q, k, out, reps)
+                    print(json.dumps({"shape": name, "Q": Q, "N": N, "k": k, "chunks_forced": chunks,
+                                      "variant": var, "plan": rb.plan(Q, k),
+                                      "search_ms": round(med, 4), "kernel_ms": round(kern, 4),
+                                      "kernel_tflops": round(flop / (kern * 1e-3) / 1e12, 1)}), flush=True)
         os.environ.pop("ZSAAC_CHUNKS", None)
+        for t in TUNABLES:
+            os.environ.pop(t, None)
         rb.close()
         del rb, q
         torch.cuda.empty_cache()

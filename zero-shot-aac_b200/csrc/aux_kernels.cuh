@@ -27,13 +27,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
-                      int64_t n_rows_out, int d, int normalize) {
+                      int64_t n_rows_out, int d, int normalize, unsigned int* __restrict__ row_thr) {
   // the consumer (fused search kernel) may begin its prologue now; it waits for this grid to
   // finish before it reads `out`
   ptx::pdl_launch_dependents();
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows_out) return;
+  // query side of a search: reset the row's shared admission threshold (SimTopkParams::row_thr)
+  if (row_thr != nullptr && lane == 0) row_thr[row] = 0u;
   OutT* dst = out + row * d;
   if (row >= n_rows) {
     // padding rows [n_rows, n_rows_out): zeros, so the consumer's TMA boxes never leave the tensor

@@ -91,7 +91,39 @@ struct SimTopkParams {
   int sync_window;            // tiles per window
   int windows_per_unit;       // ceil(tiles_per_chunk / sync_window)
   int max_iters;              // ceil(num_units / num_workers)
+  // Shared admission threshold per query row (nullable = off), TOPK mode.  Every epilogue thread
+  // publishes the k-th score of its list once the list is full (atomicMax on an order-preserving
+  // key) and starts each bank tile from the largest value published so far for its row — by the
+  // other column half, by concurrently running chunks and, above all, by chunks of the same query
+  // tile that ran earlier, so a unit that starts late does not warm its list up from -inf again.
+  // Exactness: if some list holds k entries >= t, no element scoring strictly below t can be in
+  // the global top-k, so units admit only v > pred(t) (the float just below t: elements EQUAL to
+  // t may still win the index tie-break).  Lists then may hold fewer than k entries (the rest
+  // stay -inf / IDX_SENTINEL); the merged result is the exact top-k whatever the timing.
+  unsigned int* row_thr;      // [Q padded], keys; zeroed per search by the query cast kernel
 };
+
+// Order-preserving float -> uint32 key (unsigned compare == float compare, -0 < +0), so that
+// atomicMax works on scores of either sign.  Key 0 (the zero-initialised state) and everything up
+// to key(-inf) decode to "no threshold yet".
+constexpr unsigned int KEY_NEG_INF = 0x007fffffu;
+__device__ __forceinline__ unsigned int score_key(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// The largest float strictly below the score a key encodes (-inf when nothing is published yet).
+__device__ __forceinline__ float seed_below(unsigned int key) {
+  if (key <= KEY_NEG_INF) return -CUDART_INF_F;
+  const unsigned int kk = key - 1u;
+  const float f = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+  // pred(+0) is -0, which still compares equal to +0: step once more, to the negative denormal
+  return (f == 0.0f) ? __uint_as_float(0x80000001u) : f;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 constexpr long long SYNC_WAIT_LIMIT_CYCLES = 600000;   // ~0.3-0.4 ms: then give up lock-step
 
@@ -350,6 +382,12 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (g >= 0 && c >= 0 && c < p.n_bank) self_col = static_cast<int>(c);
       }
       list.init(p.k);
+      // admission threshold = max(k-th score of this list, what the row's other lists published)
+      const bool share = (MODE == MODE_TOPK) && p.row_thr != nullptr && row < p.Q;
+      float seed = -CUDART_INF_F;
+      float published = -CUDART_INF_F;
+      unsigned int seed_key = 0;
+      if (share) seed_key = ld_relaxed_u32(p.row_thr + row);
       float thr = list.threshold();
       // RANK mode state (KCAP = target slots)
       float ts[KCAP];
@@ -374,6 +412,13 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ptx::tc_fence_after();
         if (tile_count == 0 && warp == EPI_WARP0 && lane == 0) trace_stamp(p, 2);  // first tile's MMAs done
         const int col_tile = t * BLOCK_N;
+        if constexpr (MODE == MODE_TOPK) {
+          // the key was requested one tile ago (at unit start for the first tile), so its latency
+          // is hidden behind a whole tile of scanning; the next one is requested right away
+          seed = fmaxf(seed, seed_below(seed_key));
+          thr = fmaxf(thr, seed);
+          if (share) seed_key = ld_relaxed_u32(p.row_thr + row);
+        }
 #pragma unroll 1
         for (int c0 = half * EPI_COLS; c0 < (half + 1) * EPI_COLS; c0 += 32) {
           uint32_t r[32];
@@ -428,7 +473,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 const int col = col0 + j;
                 if (v > thr && col < p.n_bank && col != self_col) {
                   list.insert(v, col);
-                  thr = list.threshold();
+                  thr = fmaxf(list.threshold(), seed);
                 }
               }
             }
@@ -441,6 +486,15 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (lane == 0) {
           if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
           else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+        }
+        if constexpr (MODE == MODE_TOPK) {
+          if (share) {
+            const float kth = list.threshold();      // > -inf only once the list holds k entries
+            if (kth > published) {
+              atomicMax(p.row_thr + row, score_key(kth));   // result unused: a fire-and-forget RED
+              published = kth;
+            }
+          }
         }
       }
       if (warp == EPI_WARP0 && lane == 0) trace_stamp(p, 3);   // last tile of the unit scanned

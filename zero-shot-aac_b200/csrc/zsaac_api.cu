@@ -79,6 +79,7 @@ struct zs_ctx {
 
   __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
   int64_t q_ws_rows = 0;
+  unsigned int* row_thr = nullptr;  // [q_ws_rows] shared admission thresholds (SimTopkParams::row_thr)
   float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
   int64_t part_elems = 0;
@@ -140,7 +141,7 @@ int pick_cta_group(const zs_ctx* ctx, int64_t Q) {
 
 // Split the bank into `chunks` contiguous runs of 256-row tiles so that (query tiles x chunks)
 // work units fill the SMs in whole waves with the least padded work.
-Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
+Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
   Plan pl{};
   const int cg = pick_cta_group(ctx, Q);
   pl.cg = cg;
@@ -156,8 +157,10 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int /*k*/) {
     if (s_eff != s) continue;  // same split as a smaller s
     const int64_t units = static_cast<int64_t>(pl.m_tiles) * s_eff;
     const int64_t waves = (units + workers - 1) / workers;
-    // per unit: tpc tiles + ~0.75 tile of list warm-up / pipeline fill / partial write-out
-    const double cost = static_cast<double>(waves) * (tpc + 0.75);
+    // per unit: tpc tiles + pipeline fill / partial write-out (~0.75 tile) + what is left of the
+    // top-k list warm-up once units share their thresholds (grows with k; fitted to the chunk
+    // sweeps in profiles/r01/sweep_chunks_*.jsonl)
+    const double cost = static_cast<double>(waves) * (tpc + 0.75 + 0.15 * k);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s_eff; }
   }
   if (const char* forced = getenv("ZSAAC_CHUNKS")) {   // tuning hook: pin the number of bank chunks
@@ -192,7 +195,9 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
   const int64_t q_pad = padded_query_rows(Q);
   if (q_pad > ctx->q_ws_rows) {
     if (ctx->q_ws) { ZS_CUDA(cudaFree(ctx->q_ws)); ctx->q_ws = nullptr; ctx->q_ws_rows = 0; }
+    if (ctx->row_thr) { ZS_CUDA(cudaFree(ctx->row_thr)); ctx->row_thr = nullptr; }
     ZS_CUDA(cudaMalloc(&ctx->q_ws, static_cast<size_t>(q_pad) * ctx->bank_d * sizeof(__nv_bfloat16)));
+    ZS_CUDA(cudaMalloc(&ctx->row_thr, static_cast<size_t>(q_pad) * sizeof(unsigned int)));
     ctx->q_ws_rows = q_pad;
   }
   const Plan pl = make_plan(ctx, Q, k);
@@ -216,10 +221,10 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
 
 template <typename InT>
 void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int64_t rows_out, int d,
-                      int normalize, cudaStream_t st) {
+                      int normalize, unsigned int* row_thr, cudaStream_t st) {
   const int64_t blocks = (rows_out * 32 + 255) / 256;
   zs::normalize_cast_kernel<InT, __nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      static_cast<const InT*>(in), out, rows, rows_out, d, normalize);
+      static_cast<const InT*>(in), out, rows, rows_out, d, normalize, row_thr);
 }
 
 
@@ -311,8 +316,10 @@ int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkPara
 int prepare_queries(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int normalize,
                     CUtensorMap* qmap, cudaStream_t st) {
   const int64_t q_pad = padded_query_rows(Q);
-  if (q_dtype == ZS_F32) launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
-  else launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
+  if (q_dtype == ZS_F32)
+    launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, ctx->row_thr, st);
+  else
+    launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, ctx->row_thr, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return encode_rows_map(ctx, qmap, ctx->q_ws, q_pad, ctx->bank_d, zs::BLOCK_M);
@@ -381,6 +388,7 @@ int zs_destroy(zs_ctx* ctx) {
   DeviceGuard guard(ctx->device);
   cudaFree(ctx->bank);
   cudaFree(ctx->q_ws);
+  cudaFree(ctx->row_thr);
   cudaFree(ctx->part_scores);
   cudaFree(ctx->part_idx);
   cudaFreeHost(ctx->err_host);
@@ -440,8 +448,8 @@ int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* dst = ctx->bank + dst_row * ctx->bank_d;
-  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
-  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
+  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, nullptr, st);
+  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, nullptr, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -548,6 +556,8 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   p.dump = nullptr;
   p.err_flag = ctx->err_flag;
   p.trace = ctx->trace;
+  const char* share_env = getenv("ZSAAC_SHARE_THR");   // tuning hook: 0 = every unit warms up alone
+  p.row_thr = (share_env && share_env[0] == '0') ? nullptr : ctx->row_thr;
   if (pl.sync_window > 0) {
     p.sync_cnt = ctx->sync_cnt;
     p.sync_window = pl.sync_window;
@@ -745,7 +755,7 @@ int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (n_rows * 32 + 255) / 256;
-  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, n_rows, d, 1);
+  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, n_rows, d, 1, nullptr);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
