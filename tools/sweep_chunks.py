@@ -28,7 +28,7 @@ SHAPES = {
 #   SWEEP_VARIANTS="ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0;ZSAAC_LOCKSTEP=0"
 VARIANTS = [dict(kv.split("=") for kv in v.split(",") if kv)
             for v in os.environ.get("SWEEP_VARIANTS", "ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0").split(";")]
-TUNABLES = ("ZSAAC_SHARE_THR", "ZSAAC_LOCKSTEP")
+TUNABLES = ("ZSAAC_SHARE_THR", "ZSAAC_LOCKSTEP", "ZSAAC_RES")
 
 
 def time_kernel(rb, q, k, out, reps):
@@ -53,6 +53,8 @@ def main():
     names = sys.argv[1:] or list(SHAPES)
     for name in names:
         Q, N, ks, chunk_list = SHAPES[name]
+        if os.environ.get("SWEEP_QUICK"):       # default plan and the first k only
+            ks, chunk_list = ks[:1], [0]
         g = torch.Generator(device=dev).manual_seed(N + Q)
         rb = zsaac_b200.RelatedBank(N, D, device=dev)
         for lo in range(0, N, 65536):

@@ -29,6 +29,19 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
+// True in exactly one (the lowest active) lane of a converged warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -34,8 +34,11 @@ constexpr int BLOCK_K = 64;    // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;
 // smem ring depth: a slot holds one K-step of operands, 48 KiB for a single CTA (16 KiB queries +
 // 32 KiB bank) and 32 KiB per CTA of a pair (16 + 16), so a pair can run 6 stages deep
+#ifndef ZS_PAIR_STAGES
+#define ZS_PAIR_STAGES 6
+#endif
 template <int CG>
-constexpr int num_stages() { return CG == 2 ? 6 : 4; }
+constexpr int num_stages() { return CG == 2 ? ZS_PAIR_STAGES : 4; }
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512: the whole tensor memory of the SM
 constexpr int EPI_WARP0 = 4;
@@ -49,9 +52,35 @@ template <int CG>
 constexpr int b_stage_bytes() { return (BLOCK_N / CG) * BLOCK_K * 2; }  // 32 KiB, or 16 KiB per CTA of a pair
 template <int CG>
 constexpr int stage_bytes() { return A_STAGE_BYTES + b_stage_bytes<CG>(); }
-constexpr int BARRIER_BYTES = 256;
-template <int CG>
-constexpr int smem_bytes() { return num_stages<CG>() * stage_bytes<CG>() + BARRIER_BYTES + 1024; }
+constexpr int BARRIER_BYTES = 512;
+// Resident-query variant (RES > 0, pairs only).  The kernel is bound by what the L2 can deliver to
+// the SMs (ncu: 11.4 TB/s of operand reads at config 3 = the LTS throughput cap, tensor pipe 80 %
+// active): every bank tile re-reads the CTA's whole 128 x d query tile.  With RES > 0 the first RES
+// 64-wide K-blocks of the query tile (RES x 16 KiB) stay in shared memory for the whole work unit
+// and only the remaining K-blocks and the bank stream through a ring of 16 KiB slots: at d = 1024
+// and RES = 8 the L2 -> SM traffic per bank tile drops from 512 to 384 KiB per CTA.
+constexpr int SLOT_BYTES = 16 * 1024;           // one 128-row x 64 bf16 block (query or bank half)
+constexpr int SMEM_LIMIT = 227 * 1024;          // opt-in maximum dynamic shared memory per CTA
+template <int RES>
+constexpr int ring_slots() { return (SMEM_LIMIT - 1024 - BARRIER_BYTES - RES * SLOT_BYTES) / SLOT_BYTES; }
+template <int CG, int RES = 0>
+constexpr int smem_bytes() {
+  return (RES == 0 ? num_stages<CG>() * stage_bytes<CG>() : (RES + ring_slots<RES>()) * SLOT_BYTES) +
+         BARRIER_BYTES + 1024;
+}
+// K-step order of the resident variant: streamed and resident K-blocks alternate (streamed first),
+// so the ring drains at an even 1.5 slots per step and a new unit's first step never waits for
+// the resident blocks of the previous one.  Step i of a tile -> (K-block, is it resident).
+struct KStep {
+  int s_next, r_next, res_eff, nkb;
+  __device__ __forceinline__ KStep(int nkb_, int res) : s_next(res < nkb_ ? res : nkb_), r_next(0),
+                                                         res_eff(res < nkb_ ? res : nkb_), nkb(nkb_) {}
+  __device__ __forceinline__ int next(int i, bool& resident) {
+    const bool stream = (s_next < nkb) && (((i & 1) == 0) || r_next >= res_eff);
+    resident = !stream;
+    return stream ? s_next++ : r_next++;
+  }
+};
 
 constexpr int IDX_SENTINEL = 0x7fffffff;
 
@@ -195,10 +224,11 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
 // the reference's retrieval metrics obtain from a full argsort (retrieval/tools/utils.py:183,236).
 enum : int { MODE_TOPK = 0, MODE_DUMP = 1, MODE_RANK = 2 };
 
-template <int KCAP, int CG, int MODE>
+template <int KCAP, int CG, int MODE, int RES = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const SimTopkParams p) {
+  static_assert(RES == 0 || CG == 2, "the resident-query variant is built for CTA pairs");
   constexpr bool DUMP = (MODE == MODE_DUMP);
   constexpr bool RANK = (MODE == MODE_RANK);
   extern __shared__ uint8_t smem_raw[];
@@ -206,22 +236,32 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base_u32 - raw_u32);
 
-  constexpr int STAGES = num_stages<CG>();
-  constexpr int STAGE_STRIDE = stage_bytes<CG>();
+  // RES == 0: ring of STAGES slots, each one K-step of operands (query block + bank block).
+  // RES  > 0: RES resident query blocks, then a ring of STAGES 16 KiB slots (one block each).
+  constexpr int STAGES = (RES == 0) ? num_stages<CG>() : ring_slots<RES>();
+  constexpr int STAGE_STRIDE = (RES == 0) ? stage_bytes<CG>() : SLOT_BYTES;
   constexpr int B_BYTES = b_stage_bytes<CG>();
   constexpr uint32_t TX_BYTES = static_cast<uint32_t>(CG) * (A_STAGE_BYTES + B_BYTES);
+  constexpr uint32_t SLOT_TX = static_cast<uint32_t>(CG) * SLOT_BYTES;   // both CTAs' blocks
+  constexpr int DATA_BYTES = RES * SLOT_BYTES + STAGES * STAGE_STRIDE;
+  static_assert(8 * (2 * STAGES + 2 * RES + 2 * ACC_STAGES) + 4 <= BARRIER_BYTES, "barrier area");
+  static_assert(DATA_BYTES + BARRIER_BYTES + 1024 <= SMEM_LIMIT, "shared memory budget");
 
-  const uint32_t bar_base = base_u32 + STAGES * STAGE_STRIDE;
+  const uint32_t ring_u32 = base_u32 + RES * SLOT_BYTES;   // resident query blocks come first
+  const uint32_t bar_base = base_u32 + DATA_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
-  uint32_t* tmem_slot =
-      reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_STRIDE + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + r); };
+  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + RES + r); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
+      smem + DATA_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES + 2 * RES));
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
-  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  // (shuffles from lane 0 tell the compiler these values are warp-uniform)
+  const uint32_t cta_rank = (CG == 2) ? __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) : 0u;
   const bool is_leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {
@@ -237,13 +277,18 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);   // one arrival per epilogue warp
     }
+    for (int r = 0; r < RES; ++r) {
+      ptx::mbar_init(rfull_bar(r), 1);
+      ptx::mbar_init(rempty_bar(r), 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_slot), TMEM_COLS);
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tmem_base =
+      __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
   if (threadIdx.x == 0) trace_stamp(p, 1);               // barriers + TMEM ready
   // Everything above overlaps the tail of the query normalise/cast kernel (programmatic
   // dependent launch); its output (the bf16 query workspace) is only touched below.
@@ -254,38 +299,49 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int num_workers = static_cast<int>(gridDim.x) / CG;
   const int num_units = p.num_m_tiles * p.num_chunks;
 
+  // The producer and the MMA issuer run their loops with the WHOLE warp (all values warp-uniform)
+  // and elect one lane only around the instructions that must be issued once.  Inside an
+  // `if (lane == 0)` region the compiler cannot use the uniform datapath, and every
+  // tcgen05.mma / TMA operand (they live in uniform registers) then costs an elect + R2UR
+  // "waterfall" loop: ~90 dependent instructions per K-step on the issuing thread, which —
+  // not the tensor pipe — capped the kernel at 80-88 % tensor duty (profiles/r01/SUMMARY.md).
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
-      uint32_t full_leader0 = full_bar(0);
-      if constexpr (CG == 2) {
-        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
-      }
-      const bool sync_on = (p.sync_cnt != nullptr) && is_leader;   // the leader paces the pair
-      bool sync_wait = sync_on;
-      int iter = 0;
-      for (int u = worker; u < num_units; u += num_workers, ++iter) {
-        const int m_tile = u % p.num_m_tiles;
-        const int chunk = u / p.num_m_tiles;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
-        const int q_row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M;
-        for (int t = t0; t < t1; ++t) {
-          const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
-          if (sync_on && (t - t0) % p.sync_window == 0) {
-            const int win = iter * p.windows_per_unit + (t - t0) / p.sync_window;
-            if (sync_wait && win > 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
+    uint32_t full_leader0 = full_bar(0);
+    if constexpr (CG == 2) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
+      full_leader0 = __shfl_sync(0xffffffffu, full_leader0, 0);
+    }
+    const bool sync_on = (p.sync_cnt != nullptr) && is_leader;   // the leader paces the pair
+    bool sync_wait = sync_on;
+    int iter = 0;
+    for (int u = worker; u < num_units; u += num_workers, ++iter) {
+      const int m_tile = u % p.num_m_tiles;
+      const int chunk = u / p.num_m_tiles;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+      const int q_row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M;
+      for (int t = t0; t < t1; ++t) {
+        const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
+        if (sync_on && (t - t0) % p.sync_window == 0) {
+          const int win = iter * p.windows_per_unit + (t - t0) / p.sync_window;
+          if (sync_wait && win > 0) {
+            int in_step = 1;
+            if (lane == 0) {
               const unsigned int* prev = p.sync_cnt + (win - 1);
               const long long w0 = clock64();
               while (ld_acquire_u32(prev) < static_cast<unsigned int>(num_workers)) {
-                if (clock64() - w0 > SYNC_WAIT_LIMIT_CYCLES) { sync_wait = false; break; }
+                if (clock64() - w0 > SYNC_WAIT_LIMIT_CYCLES) { in_step = 0; break; }
                 __nanosleep(256);
               }
             }
+            if (__shfl_sync(0xffffffffu, in_step, 0) == 0) sync_wait = false;
           }
+        }
+        if constexpr (RES == 0) {
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
             //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
@@ -293,43 +349,77 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
             const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
             const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-            if constexpr (CG == 1) {
-              ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
-              ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
-              ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
-            } else {
-              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
-              const uint32_t full_leader = full_leader0 + 8u * stage;
-              ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
-              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+            if (ptx::elect_one()) {
+              if constexpr (CG == 1) {
+                ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+                ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
+                ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+              } else {
+                if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+                const uint32_t full_leader = full_leader0 + 8u * stage;
+                ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
+                ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (sync_on && ((t - t0) % p.sync_window == p.sync_window - 1 || t == t1 - 1)) {
-            // loads of this window are issued: count this worker in
-            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + (t - t0) / p.sync_window, 1u);
+        } else {
+          // one 16 KiB block into the next free ring slot
+          auto ring_load = [&](const CUtensorMap* map, int kb, int row0) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
+            if (ptx::elect_one()) {
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), SLOT_TX);
+              ptx::tma_load_2d_cg2(ring_u32 + stage * SLOT_BYTES, map, full_leader0 + 8u * stage,
+                                   kb * BLOCK_K, row0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          };
+          KStep seq(p.num_k_blocks, RES);
+          for (int i = 0; i < p.num_k_blocks; ++i) {
+            bool resident;
+            const int kb = seq.next(i, resident);
+            if (!resident) {
+              ring_load(&tmap_q, kb, q_row);
+            } else if (t == t0) {
+              // first tile of the unit: (re)fill resident block kb once the previous unit's
+              // last MMAs on it have completed
+              ptx::mbar_wait(rempty_bar(kb), (static_cast<uint32_t>(iter) & 1u) ^ 1u, p.err_flag,
+                             ERR_PRODUCER);
+              if (ptx::elect_one()) {
+                if (is_leader) ptx::mbar_arrive_expect_tx(rfull_bar(kb), SLOT_TX);
+                ptx::tma_load_2d_cg2(base_u32 + kb * SLOT_BYTES, &tmap_q,
+                                     full_leader0 + (rfull_bar(kb) - full_bar(0)), kb * BLOCK_K, q_row);
+              }
+            }
+            ring_load(&tmap_b, kb, b_row);
           }
         }
-        if (sync_on) {   // a ragged (shorter) last chunk: count the windows this unit does not have
-          for (int w = (t1 - t0 + p.sync_window - 1) / p.sync_window; w < p.windows_per_unit; ++w)
-            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
+        if (sync_on && lane == 0 &&
+            ((t - t0) % p.sync_window == p.sync_window - 1 || t == t1 - 1)) {
+          // loads of this window are issued: count this worker in
+          atomicAdd(p.sync_cnt + iter * p.windows_per_unit + (t - t0) / p.sync_window, 1u);
         }
       }
-      if (sync_on) {     // workers with one unit fewer: count the iterations they do not run
-        for (; iter < p.max_iters; ++iter)
-          for (int w = 0; w < p.windows_per_unit; ++w)
-            atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
+      if (sync_on && lane == 0) {   // a ragged (shorter) last chunk: count the windows this unit does not have
+        for (int w = (t1 - t0 + p.sync_window - 1) / p.sync_window; w < p.windows_per_unit; ++w)
+          atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
       }
+    }
+    if (sync_on && lane == 0) {     // workers with one unit fewer: count the iterations they do not run
+      for (; iter < p.max_iters; ++iter)
+        for (int w = 0; w < p.windows_per_unit; ++w)
+          atomicAdd(p.sync_cnt + iter * p.windows_per_unit + w, 1u);
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && is_leader) {
+    if (is_leader) {
       constexpr uint32_t IDESC = ptx::make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_count = 0;
-      for (int u = worker; u < num_units; u += num_workers) {
+      int iter = 0;
+      for (int u = worker; u < num_units; u += num_workers, ++iter) {
         const int chunk = u / p.num_m_tiles;
         const int t0 = chunk * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
@@ -339,24 +429,65 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, ERR_MMA_TEMPTY);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-            ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
-            ptx::tc_fence_after();
-            const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
-            const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
-            const uint64_t b_desc = ptx::make_smem_desc_sw128(a_src + A_STAGE_BYTES);
+          if constexpr (RES == 0) {
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+              ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+              ptx::tc_fence_after();
+              const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
+              const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
+              const uint64_t b_desc = ptx::make_smem_desc_sw128(a_src + A_STAGE_BYTES);
+              if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
-              ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
-                                 static_cast<uint32_t>((kb | k) != 0));
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
+                  ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
+                                     static_cast<uint32_t>((kb | k) != 0));
+                }
+                if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
+                else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
-            else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          } else {
+            KStep seq(p.num_k_blocks, RES);
+            for (int i = 0; i < p.num_k_blocks; ++i) {
+              bool resident;
+              const int kb = seq.next(i, resident);
+              uint32_t a_src;
+              int a_stage = -1;
+              if (!resident) {
+                ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+                a_src = ring_u32 + stage * SLOT_BYTES;
+                a_stage = stage;
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              } else {
+                if (t == t0)
+                  ptx::mbar_wait(rfull_bar(kb), static_cast<uint32_t>(iter) & 1u, p.err_flag, ERR_MMA_FULL);
+                a_src = base_u32 + kb * SLOT_BYTES;
+              }
+              ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+              ptx::tc_fence_after();
+              const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
+              const uint64_t b_desc = ptx::make_smem_desc_sw128(ring_u32 + stage * SLOT_BYTES);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
+                                     static_cast<uint32_t>((i | k) != 0));
+                }
+                // slots (and, on the unit's last tile, the resident block) are free once these
+                // MMAs have completed
+                if (a_stage >= 0) ptx::umma_commit_cg2(empty_bar(a_stage), 0b11);
+                else if (t == t1 - 1) ptx::umma_commit_cg2(rempty_bar(kb), 0b11);
+                ptx::umma_commit_cg2(empty_bar(stage), 0b11);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
-          if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));
-          else ptx::umma_commit_cg2(tfull_bar(acc), 0b11);
+          if (ptx::elect_one()) {
+            if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));
+            else ptx::umma_commit_cg2(tfull_bar(acc), 0b11);
+          }
         }
       }
     }
