@@ -102,20 +102,35 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 
 // Bounded wait: a pipeline bug must end in a trap (an error the host sees), never in a hung GPU.
-// `err` receives a code identifying the waiting role before the trap.
-#ifndef ZS_WAIT_TIMEOUT_CYCLES
-#define ZS_WAIT_TIMEOUT_CYCLES (1ll << 32)
+// `err` (nullable, mapped host memory) receives a code identifying the waiting role before the
+// trap.  The whole retry loop is ONE asm statement: the compiler sees straight-line code, so the
+// warps that wait and then issue TMA / tcgen05 instructions keep warp-uniform control flow (a
+// C++ retry loop on the asm's result looks divergent to it and pushes every uniform-register
+// operand through an elect + R2UR loop).  Each failed try_wait suspends the warp for a
+// hardware-defined time slice, so ZS_WAIT_MAX_TRIES bounds the wait at seconds, not cycles.
+#ifndef ZS_WAIT_MAX_TRIES
+#define ZS_WAIT_MAX_TRIES (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > ZS_WAIT_TIMEOUT_CYCLES) {
-      if (err) *reinterpret_cast<volatile int*>(err) = code;   // mapped host memory
-      __threadfence_system();
-      __trap();
-    }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, has_err;\n\t"
+      ".reg .u32 tries;\n\t"
+      "mov.u32 tries, 0;\n\t"
+      "ZS_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ZS_WAIT_DONE;\n\t"
+      "add.u32 tries, tries, 1;\n\t"
+      "setp.lt.u32 q, tries, %4;\n\t"
+      "@q bra ZS_WAIT_LOOP;\n\t"
+      "setp.ne.u64 has_err, %2, 0;\n\t"
+      "@has_err st.volatile.global.u32 [%2], %3;\n\t"
+      "fence.sc.sys;\n\t"
+      "trap;\n\t"
+      "ZS_WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "l"(reinterpret_cast<uint64_t>(err)), "r"(code), "n"(ZS_WAIT_MAX_TRIES)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- TMA

@@ -71,6 +71,23 @@ constexpr int smem_bytes() {
 // K-step order of the resident variant: streamed and resident K-blocks alternate (streamed first),
 // so the ring drains at an even 1.5 slots per step and a new unit's first step never waits for
 // the resident blocks of the previous one.  Step i of a tile -> (K-block, is it resident).
+// Position in the slot ring of the resident variant.  Generic: loop-carried (stage, phase).
+// Unrolled (NKB > 0, the number of K-blocks is a compile-time constant and a bank tile uses the
+// ring a whole, even number of times): every tile starts at slot 0 with parity 0, so after full
+// unrolling slot index and parity of every load are literals and the issuing warps' loops shrink
+// to waits, issues and commits.
+template <int STAGES, bool UNROLLED>
+struct RingPos {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void tile_start() {
+    if constexpr (UNROLLED) { stage = 0; phase = 0; }
+  }
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  }
+};
+
 struct KStep {
   int s_next, r_next, res_eff, nkb;
   __device__ __forceinline__ KStep(int nkb_, int res) : s_next(res < nkb_ ? res : nkb_), r_next(0),
@@ -224,11 +241,13 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
 // the reference's retrieval metrics obtain from a full argsort (retrieval/tools/utils.py:183,236).
 enum : int { MODE_TOPK = 0, MODE_DUMP = 1, MODE_RANK = 2 };
 
-template <int KCAP, int CG, int MODE, int RES = 0>
+template <int KCAP, int CG, int MODE, int RES = 0, int NKB = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const SimTopkParams p) {
   static_assert(RES == 0 || CG == 2, "the resident-query variant is built for CTA pairs");
+  static_assert(NKB == 0 || RES > 0, "the unrolled K loop belongs to the resident-query variant");
+  constexpr bool UNROLLED = NKB > 0;
   constexpr bool DUMP = (MODE == MODE_DUMP);
   constexpr bool RANK = (MODE == MODE_RANK);
   extern __shared__ uint8_t smem_raw[];
@@ -246,6 +265,9 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int DATA_BYTES = RES * SLOT_BYTES + STAGES * STAGE_STRIDE;
   static_assert(8 * (2 * STAGES + 2 * RES + 2 * ACC_STAGES) + 4 <= BARRIER_BYTES, "barrier area");
   static_assert(DATA_BYTES + BARRIER_BYTES + 1024 <= SMEM_LIMIT, "shared memory budget");
+  // unrolled: slot uses per bank tile = 2 per streamed K-block + 1 per resident one
+  static_assert(!UNROLLED || (NKB > RES && (2 * (NKB - RES) + RES) % (2 * STAGES) == 0),
+                "a bank tile must walk the ring a whole, even number of times");
 
   const uint32_t ring_u32 = base_u32 + RES * SLOT_BYTES;   // resident query blocks come first
   const uint32_t bar_base = base_u32 + DATA_BYTES;
@@ -309,6 +331,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    RingPos<STAGES, UNROLLED> ring;      // resident variant
     // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
     uint32_t full_leader0 = full_bar(0);
     if constexpr (CG == 2) {
@@ -366,16 +389,19 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         } else {
           // one 16 KiB block into the next free ring slot
           auto ring_load = [&](const CUtensorMap* map, int kb, int row0) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
+            ptx::mbar_wait(empty_bar(ring.stage), ring.phase ^ 1u, p.err_flag, ERR_PRODUCER);
             if (ptx::elect_one()) {
-              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), SLOT_TX);
-              ptx::tma_load_2d_cg2(ring_u32 + stage * SLOT_BYTES, map, full_leader0 + 8u * stage,
-                                   kb * BLOCK_K, row0);
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(ring.stage), SLOT_TX);
+              ptx::tma_load_2d_cg2(ring_u32 + ring.stage * SLOT_BYTES, map,
+                                   full_leader0 + 8u * ring.stage, kb * BLOCK_K, row0);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            ring.advance();
           };
-          KStep seq(p.num_k_blocks, RES);
-          for (int i = 0; i < p.num_k_blocks; ++i) {
+          const int nkb = UNROLLED ? NKB : p.num_k_blocks;
+          KStep seq(nkb, RES);
+          ring.tile_start();
+#pragma unroll
+          for (int i = 0; i < nkb; ++i) {
             bool resident;
             const int kb = seq.next(i, resident);
             if (!resident) {
@@ -417,6 +443,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       constexpr uint32_t IDESC = ptx::make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
+      RingPos<STAGES, UNROLLED> ring;    // resident variant
       uint32_t tile_count = 0;
       int iter = 0;
       for (int u = worker; u < num_units; u += num_workers, ++iter) {
@@ -449,26 +476,29 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
           } else {
-            KStep seq(p.num_k_blocks, RES);
-            for (int i = 0; i < p.num_k_blocks; ++i) {
+            const int nkb = UNROLLED ? NKB : p.num_k_blocks;
+            KStep seq(nkb, RES);
+            ring.tile_start();
+#pragma unroll
+            for (int i = 0; i < nkb; ++i) {
               bool resident;
               const int kb = seq.next(i, resident);
               uint32_t a_src;
               int a_stage = -1;
               if (!resident) {
-                ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
-                a_src = ring_u32 + stage * SLOT_BYTES;
-                a_stage = stage;
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                ptx::mbar_wait(full_bar(ring.stage), ring.phase, p.err_flag, ERR_MMA_FULL);
+                a_src = ring_u32 + ring.stage * SLOT_BYTES;
+                a_stage = ring.stage;
+                ring.advance();
               } else {
                 if (t == t0)
                   ptx::mbar_wait(rfull_bar(kb), static_cast<uint32_t>(iter) & 1u, p.err_flag, ERR_MMA_FULL);
                 a_src = base_u32 + kb * SLOT_BYTES;
               }
-              ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+              ptx::mbar_wait(full_bar(ring.stage), ring.phase, p.err_flag, ERR_MMA_FULL);
               ptx::tc_fence_after();
               const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
-              const uint64_t b_desc = ptx::make_smem_desc_sw128(ring_u32 + stage * SLOT_BYTES);
+              const uint64_t b_desc = ptx::make_smem_desc_sw128(ring_u32 + ring.stage * SLOT_BYTES);
               if (ptx::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -479,9 +509,9 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 // MMAs have completed
                 if (a_stage >= 0) ptx::umma_commit_cg2(empty_bar(a_stage), 0b11);
                 else if (t == t1 - 1) ptx::umma_commit_cg2(rempty_bar(kb), 0b11);
-                ptx::umma_commit_cg2(empty_bar(stage), 0b11);
+                ptx::umma_commit_cg2(empty_bar(ring.stage), 0b11);
               }
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              ring.advance();
             }
           }
           if (ptx::elect_one()) {
