@@ -8,8 +8,10 @@
 // Shape of the contraction:  M = query rows, N = bank rows, K = embedding dim (bf16, fp32 acc).
 //   * warp 0   : TMA producer  — streams 128x64 query blocks and 256x64 bank blocks (128-byte
 //                swizzle) through a STAGES-deep shared-memory ring
-//   * warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128*CG, N=256, K=16) into one of
-//                two 256-column TMEM accumulators
+//   * warp 1   : MMA issuer    — issues tcgen05.mma (M=128*CG, N=256, K=16) into one of two
+//                256-column TMEM accumulators
+//                (both walk their loops with the whole warp, warp-uniformly, and elect one lane
+//                per issue: the operands then live in uniform registers)
 //   * warp 2   : TMEM allocator
 //   * warps 4-11: epilogue     — two warps per TMEM lane quarter; thread t of warp w owns query row
 //                32*(w%4)+t and the 128-column half (w-4)/4 of every bank tile: it reads its
@@ -52,52 +54,9 @@ template <int CG>
 constexpr int b_stage_bytes() { return (BLOCK_N / CG) * BLOCK_K * 2; }  // 32 KiB, or 16 KiB per CTA of a pair
 template <int CG>
 constexpr int stage_bytes() { return A_STAGE_BYTES + b_stage_bytes<CG>(); }
-constexpr int BARRIER_BYTES = 512;
-// Resident-query variant (RES > 0, pairs only).  The kernel is bound by what the L2 can deliver to
-// the SMs (ncu: 11.4 TB/s of operand reads at config 3 = the LTS throughput cap, tensor pipe 80 %
-// active): every bank tile re-reads the CTA's whole 128 x d query tile.  With RES > 0 the first RES
-// 64-wide K-blocks of the query tile (RES x 16 KiB) stay in shared memory for the whole work unit
-// and only the remaining K-blocks and the bank stream through a ring of 16 KiB slots: at d = 1024
-// and RES = 8 the L2 -> SM traffic per bank tile drops from 512 to 384 KiB per CTA.
-constexpr int SLOT_BYTES = 16 * 1024;           // one 128-row x 64 bf16 block (query or bank half)
-constexpr int SMEM_LIMIT = 227 * 1024;          // opt-in maximum dynamic shared memory per CTA
-template <int RES>
-constexpr int ring_slots() { return (SMEM_LIMIT - 1024 - BARRIER_BYTES - RES * SLOT_BYTES) / SLOT_BYTES; }
-template <int CG, int RES = 0>
-constexpr int smem_bytes() {
-  return (RES == 0 ? num_stages<CG>() * stage_bytes<CG>() : (RES + ring_slots<RES>()) * SLOT_BYTES) +
-         BARRIER_BYTES + 1024;
-}
-// K-step order of the resident variant: streamed and resident K-blocks alternate (streamed first),
-// so the ring drains at an even 1.5 slots per step and a new unit's first step never waits for
-// the resident blocks of the previous one.  Step i of a tile -> (K-block, is it resident).
-// Position in the slot ring of the resident variant.  Generic: loop-carried (stage, phase).
-// Unrolled (NKB > 0, the number of K-blocks is a compile-time constant and a bank tile uses the
-// ring a whole, even number of times): every tile starts at slot 0 with parity 0, so after full
-// unrolling slot index and parity of every load are literals and the issuing warps' loops shrink
-// to waits, issues and commits.
-template <int STAGES, bool UNROLLED>
-struct RingPos {
-  int stage = 0;
-  uint32_t phase = 0;
-  __device__ __forceinline__ void tile_start() {
-    if constexpr (UNROLLED) { stage = 0; phase = 0; }
-  }
-  __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-  }
-};
-
-struct KStep {
-  int s_next, r_next, res_eff, nkb;
-  __device__ __forceinline__ KStep(int nkb_, int res) : s_next(res < nkb_ ? res : nkb_), r_next(0),
-                                                         res_eff(res < nkb_ ? res : nkb_), nkb(nkb_) {}
-  __device__ __forceinline__ int next(int i, bool& resident) {
-    const bool stream = (s_next < nkb) && (((i & 1) == 0) || r_next >= res_eff);
-    resident = !stream;
-    return stream ? s_next++ : r_next++;
-  }
-};
+constexpr int BARRIER_BYTES = 256;
+template <int CG>
+constexpr int smem_bytes() { return num_stages<CG>() * stage_bytes<CG>() + BARRIER_BYTES + 1024; }
 
 constexpr int IDX_SENTINEL = 0x7fffffff;
 
@@ -241,13 +200,10 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
 // the reference's retrieval metrics obtain from a full argsort (retrieval/tools/utils.py:183,236).
 enum : int { MODE_TOPK = 0, MODE_DUMP = 1, MODE_RANK = 2 };
 
-template <int KCAP, int CG, int MODE, int RES = 0, int NKB = 0>
+template <int KCAP, int CG, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const SimTopkParams p) {
-  static_assert(RES == 0 || CG == 2, "the resident-query variant is built for CTA pairs");
-  static_assert(NKB == 0 || RES > 0, "the unrolled K loop belongs to the resident-query variant");
-  constexpr bool UNROLLED = NKB > 0;
   constexpr bool DUMP = (MODE == MODE_DUMP);
   constexpr bool RANK = (MODE == MODE_RANK);
   extern __shared__ uint8_t smem_raw[];
@@ -255,30 +211,19 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base_u32 - raw_u32);
 
-  // RES == 0: ring of STAGES slots, each one K-step of operands (query block + bank block).
-  // RES  > 0: RES resident query blocks, then a ring of STAGES 16 KiB slots (one block each).
-  constexpr int STAGES = (RES == 0) ? num_stages<CG>() : ring_slots<RES>();
-  constexpr int STAGE_STRIDE = (RES == 0) ? stage_bytes<CG>() : SLOT_BYTES;
+  constexpr int STAGES = num_stages<CG>();
+  constexpr int STAGE_STRIDE = stage_bytes<CG>();
   constexpr int B_BYTES = b_stage_bytes<CG>();
   constexpr uint32_t TX_BYTES = static_cast<uint32_t>(CG) * (A_STAGE_BYTES + B_BYTES);
-  constexpr uint32_t SLOT_TX = static_cast<uint32_t>(CG) * SLOT_BYTES;   // both CTAs' blocks
-  constexpr int DATA_BYTES = RES * SLOT_BYTES + STAGES * STAGE_STRIDE;
-  static_assert(8 * (2 * STAGES + 2 * RES + 2 * ACC_STAGES) + 4 <= BARRIER_BYTES, "barrier area");
-  static_assert(DATA_BYTES + BARRIER_BYTES + 1024 <= SMEM_LIMIT, "shared memory budget");
-  // unrolled: slot uses per bank tile = 2 per streamed K-block + 1 per resident one
-  static_assert(!UNROLLED || (NKB > RES && (2 * (NKB - RES) + RES) % (2 * STAGES) == 0),
-                "a bank tile must walk the ring a whole, even number of times");
+  static_assert(8 * (2 * STAGES + 2 * ACC_STAGES) + 4 <= BARRIER_BYTES, "barrier area");
 
-  const uint32_t ring_u32 = base_u32 + RES * SLOT_BYTES;   // resident query blocks come first
-  const uint32_t bar_base = base_u32 + DATA_BYTES;
+  const uint32_t bar_base = base_u32 + STAGES * STAGE_STRIDE;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
-  auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + r); };
-  auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + RES + r); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
-      smem + DATA_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES + 2 * RES));
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_STRIDE + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
@@ -298,10 +243,6 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);   // one arrival per epilogue warp
-    }
-    for (int r = 0; r < RES; ++r) {
-      ptx::mbar_init(rfull_bar(r), 1);
-      ptx::mbar_init(rempty_bar(r), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -331,7 +272,6 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    RingPos<STAGES, UNROLLED> ring;      // resident variant
     // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
     uint32_t full_leader0 = full_bar(0);
     if constexpr (CG == 2) {
@@ -364,61 +304,26 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (__shfl_sync(0xffffffffu, in_step, 0) == 0) sync_wait = false;
           }
         }
-        if constexpr (RES == 0) {
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-            // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
-            //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
-            //  only look-ahead)
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
-            const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
-            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-            if (ptx::elect_one()) {
-              if constexpr (CG == 1) {
-                ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
-                ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
-                ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
-              } else {
-                if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
-                const uint32_t full_leader = full_leader0 + 8u * stage;
-                ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
-                ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
-              }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
+          //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
+          //  only look-ahead)
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
+          const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          if (ptx::elect_one()) {
+            if constexpr (CG == 1) {
+              ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
+              ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+            } else {
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              const uint32_t full_leader = full_leader0 + 8u * stage;
+              ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
+              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-        } else {
-          // one 16 KiB block into the next free ring slot
-          auto ring_load = [&](const CUtensorMap* map, int kb, int row0) {
-            ptx::mbar_wait(empty_bar(ring.stage), ring.phase ^ 1u, p.err_flag, ERR_PRODUCER);
-            if (ptx::elect_one()) {
-              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(ring.stage), SLOT_TX);
-              ptx::tma_load_2d_cg2(ring_u32 + ring.stage * SLOT_BYTES, map,
-                                   full_leader0 + 8u * ring.stage, kb * BLOCK_K, row0);
-            }
-            ring.advance();
-          };
-          const int nkb = UNROLLED ? NKB : p.num_k_blocks;
-          KStep seq(nkb, RES);
-          ring.tile_start();
-#pragma unroll
-          for (int i = 0; i < nkb; ++i) {
-            bool resident;
-            const int kb = seq.next(i, resident);
-            if (!resident) {
-              ring_load(&tmap_q, kb, q_row);
-            } else if (t == t0) {
-              // first tile of the unit: (re)fill resident block kb once the previous unit's
-              // last MMAs on it have completed
-              ptx::mbar_wait(rempty_bar(kb), (static_cast<uint32_t>(iter) & 1u) ^ 1u, p.err_flag,
-                             ERR_PRODUCER);
-              if (ptx::elect_one()) {
-                if (is_leader) ptx::mbar_arrive_expect_tx(rfull_bar(kb), SLOT_TX);
-                ptx::tma_load_2d_cg2(base_u32 + kb * SLOT_BYTES, &tmap_q,
-                                     full_leader0 + (rfull_bar(kb) - full_bar(0)), kb * BLOCK_K, q_row);
-              }
-            }
-            ring_load(&tmap_b, kb, b_row);
-          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (sync_on && lane == 0 &&
             ((t - t0) % p.sync_window == p.sync_window - 1 || t == t1 - 1)) {
@@ -443,10 +348,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       constexpr uint32_t IDESC = ptx::make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      RingPos<STAGES, UNROLLED> ring;    // resident variant
       uint32_t tile_count = 0;
-      int iter = 0;
-      for (int u = worker; u < num_units; u += num_workers, ++iter) {
+      for (int u = worker; u < num_units; u += num_workers) {
         const int chunk = u / p.num_m_tiles;
         const int t0 = chunk * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
@@ -456,63 +359,23 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, ERR_MMA_TEMPTY);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-          if constexpr (RES == 0) {
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-              ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
-              ptx::tc_fence_after();
-              const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
-              const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
-              const uint64_t b_desc = ptx::make_smem_desc_sw128(a_src + A_STAGE_BYTES);
-              if (ptx::elect_one()) {
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
+            ptx::tc_fence_after();
+            const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
+            const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
+            const uint64_t b_desc = ptx::make_smem_desc_sw128(a_src + A_STAGE_BYTES);
+            if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                  // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
-                  ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
-                                     static_cast<uint32_t>((kb | k) != 0));
-                }
-                if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
-                else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
+                ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
+                                   static_cast<uint32_t>((kb | k) != 0));
               }
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
+              else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
             }
-          } else {
-            const int nkb = UNROLLED ? NKB : p.num_k_blocks;
-            KStep seq(nkb, RES);
-            ring.tile_start();
-#pragma unroll
-            for (int i = 0; i < nkb; ++i) {
-              bool resident;
-              const int kb = seq.next(i, resident);
-              uint32_t a_src;
-              int a_stage = -1;
-              if (!resident) {
-                ptx::mbar_wait(full_bar(ring.stage), ring.phase, p.err_flag, ERR_MMA_FULL);
-                a_src = ring_u32 + ring.stage * SLOT_BYTES;
-                a_stage = ring.stage;
-                ring.advance();
-              } else {
-                if (t == t0)
-                  ptx::mbar_wait(rfull_bar(kb), static_cast<uint32_t>(iter) & 1u, p.err_flag, ERR_MMA_FULL);
-                a_src = base_u32 + kb * SLOT_BYTES;
-              }
-              ptx::mbar_wait(full_bar(ring.stage), ring.phase, p.err_flag, ERR_MMA_FULL);
-              ptx::tc_fence_after();
-              const uint64_t a_desc = ptx::make_smem_desc_sw128(a_src);
-              const uint64_t b_desc = ptx::make_smem_desc_sw128(ring_u32 + ring.stage * SLOT_BYTES);
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                  ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
-                                     static_cast<uint32_t>((i | k) != 0));
-                }
-                // slots (and, on the unit's last tile, the resident block) are free once these
-                // MMAs have completed
-                if (a_stage >= 0) ptx::umma_commit_cg2(empty_bar(a_stage), 0b11);
-                else if (t == t1 - 1) ptx::umma_commit_cg2(rempty_bar(kb), 0b11);
-                ptx::umma_commit_cg2(empty_bar(ring.stage), 0b11);
-              }
-              ring.advance();
-            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
           if (ptx::elect_one()) {
             if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));

@@ -255,11 +255,11 @@ cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t sc
                             index_stride, Q, k, idx_offset, out_scores, out_idx);
 }
 
-template <int KCAP, int CG, int MODE, int RES = 0, int NKB = 0>
+template <int KCAP, int CG, int MODE>
 int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
                    cudaStream_t st) {
-  auto kern = zs::zs_simtopk_kernel<KCAP, CG, MODE, RES, NKB>;
-  const int smem = zs::smem_bytes<CG, RES>();
+  auto kern = zs::zs_simtopk_kernel<KCAP, CG, MODE>;
+  const int smem = zs::smem_bytes<CG>();
   static bool smem_opt_in[64] = {};   // per instantiation and device: opt in to > 48 KiB once
   if (ctx->device >= 64 || !smem_opt_in[ctx->device]) {
     ZS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -298,12 +298,6 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   return ZS_OK;
 }
 
-#ifndef ZS_RES_KBLOCKS
-#define ZS_RES_KBLOCKS 8
-#endif
-constexpr int kResidentKBlocks = ZS_RES_KBLOCKS;   // 8 x 16 KiB = half of a 128 x 1024 bf16 query tile
-constexpr bool kResidentDefault = false;
-
 template <int CG>
 int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
                      bool dump, cudaStream_t st) {
@@ -311,26 +305,6 @@ int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkPara
   if (p.part_counts != nullptr)   // rank mode: KCAP = target slots
     return p.n_targets <= 1 ? launch_simtopk<1, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st)
                             : launch_simtopk<8, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st);
-  if constexpr (CG == 2) {
-    // pairs: keep the first kResidentKBlocks K-blocks of the query tile in shared memory
-    // (tuning hook ZSAAC_RES=0 streams everything, as single CTAs always do)
-    const char* res_env = getenv("ZSAAC_RES");
-    const int res_mode = res_env ? atoi(res_env) : (kResidentDefault ? 2 : 0);
-    if (res_mode >= 2 && p.num_k_blocks == 16) {   // d = 1024: K loop unrolled, ring positions literal
-      switch (kcap_for(p.k)) {
-        case 8: return launch_simtopk<8, 2, zs::MODE_TOPK, kResidentKBlocks, 16>(ctx, qmap, p, ctas, st);
-        case 16: return launch_simtopk<16, 2, zs::MODE_TOPK, kResidentKBlocks, 16>(ctx, qmap, p, ctas, st);
-        default: return launch_simtopk<32, 2, zs::MODE_TOPK, kResidentKBlocks, 16>(ctx, qmap, p, ctas, st);
-      }
-    }
-    if (res_mode >= 1) {
-      switch (kcap_for(p.k)) {
-        case 8: return launch_simtopk<8, 2, zs::MODE_TOPK, kResidentKBlocks>(ctx, qmap, p, ctas, st);
-        case 16: return launch_simtopk<16, 2, zs::MODE_TOPK, kResidentKBlocks>(ctx, qmap, p, ctas, st);
-        default: return launch_simtopk<32, 2, zs::MODE_TOPK, kResidentKBlocks>(ctx, qmap, p, ctas, st);
-      }
-    }
-  }
   switch (kcap_for(p.k)) {
     case 8: return launch_simtopk<8, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
     case 16: return launch_simtopk<16, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
