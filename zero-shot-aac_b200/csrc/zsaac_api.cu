@@ -179,9 +179,13 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
   // is much larger than what stays in L2 between the fastest and the slowest worker.
   const char* sync_env = getenv("ZSAAC_LOCKSTEP");
   const bool sync_allowed = !(sync_env && sync_env[0] == '0');
-  if (sync_allowed && pl.m_tiles > 1 && n_workers > 1 && pl.tiles_per_chunk >= 4 * kSyncWindowTiles) {
-    pl.sync_window = kSyncWindowTiles;
-    pl.windows_per_unit = (pl.tiles_per_chunk + kSyncWindowTiles - 1) / kSyncWindowTiles;
+  int window = kSyncWindowTiles;
+  if (const char* w = getenv("ZSAAC_SYNC_WINDOW")) {   // tuning hook: tiles per lock-step window
+    if (atoi(w) >= 1) window = atoi(w);
+  }
+  if (sync_allowed && pl.m_tiles > 1 && n_workers > 1 && pl.tiles_per_chunk >= 4 * window) {
+    pl.sync_window = window;
+    pl.windows_per_unit = (pl.tiles_per_chunk + window - 1) / window;
     pl.max_iters = static_cast<int>((units + n_workers - 1) / n_workers);
   }
   return pl;
