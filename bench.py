@@ -362,12 +362,19 @@ def run_ours(args):
                     "frac": gbs / peaks["hbm_gbs"], "peak_kind": f"copy bandwidth, {peaks_src}"}
     roofline["kernel"] = "zs_simtopk_kernel"
     roofline["kernel_ms"] = k_ms
+    if world > 1:
+        # every step ends in an all-gather, so the slowest rank's kernel sets the step time
+        per_rank = torch.zeros(world, device=device)
+        per_rank[rank] = k_ms
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        roofline["kernel_ms_per_rank"] = [round(v, 3) for v in per_rank.tolist()]
     roofline["kernel_share_of_step"] = k_ms / ms_per_step
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     roofline["traffic"] = None
     try:
-        with open(traffic_path) as f:
-            roofline["traffic"] = json.load(f).get(name)
+        if world == 1:          # captured with ncu on one GPU holding the whole bank
+            with open(traffic_path) as f:
+                roofline["traffic"] = json.load(f).get(name)
     except Exception:
         pass
 

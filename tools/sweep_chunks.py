@@ -21,6 +21,8 @@ SHAPES = {
     "k32": (16384, 400_000, [32, 10, 1], [0, 4, 9]),
     "audiocaps": (975, 49838, [10, 1, 32], [0, 24]),
     "clotho": (1045, 19195, [5, 1], [0]),
+    "hbm128": (128, 400_000, [10, 32], [0]),                              # HBM-bound: bank stream
+    "hbm1": (1, 400_000, [10], [0]),
 }
 
 
