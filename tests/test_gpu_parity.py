@@ -293,6 +293,89 @@ def test_wavcaps_scale_properties(zs):
     rbp.close()
 
 
+def _gpu_free_gb():
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2 ** 30
+
+
+def test_synthetic_10m_scale_properties(zs):
+    """BASELINE config 4 at full size (65,536 queries x 10 M-row bank, k=32) through properties:
+    planted rows come back first, lists are sorted / distinct / in range, the search is
+    idempotent, and a 48-query sample is re-scored against the whole bank in fp32 blocks."""
+    if _gpu_free_gb() < 60:
+        pytest.skip("needs ~30 GB of free HBM")
+    N, Q, k, blk = 10_000_000, 65_536, 32, 65_536
+    dev = torch.device("cuda")
+
+    def block(bi):
+        g = torch.Generator(device=dev).manual_seed(204 * 2 ** 32 + bi)
+        return torch.randn(min(blk, N - bi * blk), 1024, device=dev, generator=g)
+
+    rb = zs.RelatedBank(N, 1024, device=dev)
+    for bi in range(-(-N // blk)):
+        rb.upload(block(bi), bi * blk)
+    gq = torch.Generator(device=dev).manual_seed(104)
+    q = torch.randn(Q, 1024, device=dev, generator=gq)
+    planted = torch.randint(0, N, (256,), device=dev, generator=gq)
+    for j, r in enumerate(planted.tolist()):            # query j is (a scaled copy of) bank row r
+        q[j] = 2.5 * block(r // blk)[r % blk]
+    s, i = rb.search(q, k)
+    s2, i2 = rb.search(q, k)
+    torch.cuda.synchronize()
+    assert torch.equal(s, s2) and torch.equal(i, i2)
+    assert (i[:256, 0] == planted).all() and (s[:256, 0] > 0.995).all()
+    assert (s[:, 1:] <= s[:, :-1]).all() and ((i >= 0) & (i < N)).all()
+    assert (torch.sort(i, dim=1).values.diff(dim=1) != 0).all()
+    # fp32 re-scoring of a sample against every bank block (the oracle's arithmetic, blocked)
+    rows = torch.cat([torch.arange(300, 324), torch.arange(Q - 24, Q)]).to(dev)
+    qs = torch.nn.functional.normalize(q[rows], dim=-1)
+    best_s = torch.full((rows.numel(), k), -float("inf"), device=dev)
+    best_i = torch.zeros((rows.numel(), k), dtype=torch.int64, device=dev)
+    for bi in range(-(-N // blk)):
+        sc = qs @ torch.nn.functional.normalize(block(bi), dim=-1).T
+        cs, ci = sc.topk(k, dim=1)
+        ms, sel = torch.cat([best_s, cs], 1).topk(k, dim=1)
+        best_i = torch.cat([best_i, ci + bi * blk], 1).gather(1, sel)
+        best_s = ms
+    got_s, got_i = s[rows], i[rows]
+    assert (got_s - best_s).abs().max().item() <= SCORE_TOL
+    kth = best_s[:, -1:]
+    clear = best_s > kth + SCORE_TOL                     # oracle entries clearly inside the top-k
+    present = (best_i.unsqueeze(2) == got_i.unsqueeze(1)).any(dim=2)
+    assert (present | ~clear).all()
+    rb.close()
+
+
+def test_allpairs_400k_self_exclusion_properties(zs):
+    """BASELINE config 5 at full size: 400 k noise-injected bank rows as queries against the
+    same bank, self-exclusion, k=5 (reference utils.py:19-31 for the noise)."""
+    if _gpu_free_gb() < 20:
+        pytest.skip("needs ~10 GB of free HBM")
+    N, k = 400_000, 5
+    g = torch.Generator(device="cuda").manual_seed(105)
+    b = torch.nn.functional.normalize(torch.randn(N, 1024, device="cuda", generator=g), dim=-1)
+    b[7] = b[3]                                          # a twin: each must find the other first
+    q = b + torch.randn(N, 1024, device="cuda", generator=g) * (0.001 ** 0.5)
+    self_index = torch.arange(N, device="cuda")
+    rb = zs.RelatedBank.from_tensor(b)
+    s, i = rb.search(q, k, self_index=self_index)
+    torch.cuda.synchronize()
+    assert not (i == self_index[:, None]).any()
+    assert i[3, 0].item() == 7 and i[7, 0].item() == 3
+    assert (s[:, 1:] <= s[:, :-1]).all() and ((i >= 0) & (i < N)).all()
+    assert (torch.sort(i, dim=1).values.diff(dim=1) != 0).all()
+    ex = slice(1000, 5096)                               # (clear of the twins)
+    s_in, i_in = rb.search(q[ex], k + 1)                 # without exclusion the row itself is slot 0
+    torch.cuda.synchronize()
+    assert (i_in[:, 0] == self_index[ex]).all()
+    assert torch.equal(i_in[:, 1:], i[ex]) and torch.equal(s_in[:, 1:], s[ex])
+    sl = slice(200_000, 200_256)
+    rep = oracle.check_topk(s[sl].cpu(), i[sl].cpu(), q[sl].cpu(), b.cpu(), k,
+                            self_index=self_index[sl].cpu())
+    assert rep["ok"], rep
+    rb.close()
+
+
 # ------------------------------------------------------------------ shared admission thresholds
 @pytest.mark.parametrize("Q,N,k,chunks", [(300, 40_000, 10, 150), (700, 60_000, 32, 200),
                                           (129, 30_000, 5, 117), (975, 49_838, 10, 0),
