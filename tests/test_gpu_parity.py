@@ -101,6 +101,19 @@ def test_topk_matches_oracle(zs, cta_group, Q, N, k):
     assert (i == wi).float().mean().item() > 0.999
 
 
+@pytest.mark.parametrize("k", [1, 2, 7, 8, 9, 11, 12, 13, 16, 17, 23, 24, 25, 31, 32])
+def test_every_list_size(zs, cta_group, k):
+    """The register list has 8 / 12 / 16 / 24 / 32 physical slots (unused ones pinned with +inf):
+    every k around those boundaries, on a bank with duplicated rows (exact ties)."""
+    q, b = helpers.seeded((260, 1024), 70 + k), helpers.seeded((9000, 1024), 71 + k)
+    b[4000:4100] = b[100:200]                                  # exact duplicates: ties by index
+    s, i = run_search(zs, q, b, k)
+    ws, wi = oracle.stable_topk(bf16_scores(q, b), k)
+    assert (s - ws).abs().max().item() < BF16_TOL
+    assert (i == wi).float().mean().item() > 0.999
+    assert oracle.check_topk(s, i, q, b, k)["ok"]
+
+
 def test_k_equals_n(zs, cta_group):
     q, b = helpers.seeded((5, 1024), 1), helpers.seeded((20, 1024), 2)
     s, i = run_search(zs, q, b, 20)

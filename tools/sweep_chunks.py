@@ -30,7 +30,7 @@ SHAPES = {
 #   SWEEP_VARIANTS="ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0;ZSAAC_LOCKSTEP=0"
 VARIANTS = [dict(kv.split("=") for kv in v.split(",") if kv)
             for v in os.environ.get("SWEEP_VARIANTS", "ZSAAC_SHARE_THR=1;ZSAAC_SHARE_THR=0").split(";")]
-TUNABLES = ("ZSAAC_SHARE_THR", "ZSAAC_LOCKSTEP", "ZSAAC_SYNC_WINDOW")
+TUNABLES = ("ZSAAC_SHARE_THR", "ZSAAC_LOCKSTEP", "ZSAAC_SYNC_WINDOW", "ZSAAC_KCAP_POW2")
 
 
 def time_kernel(rb, q, k, out, reps):

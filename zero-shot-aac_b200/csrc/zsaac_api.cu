@@ -122,7 +122,14 @@ int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t row
   return ZS_OK;
 }
 
-int kcap_for(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
+// Physical slots of the register-resident top-k list: an insert costs ~5 instructions per slot,
+// so the list is sized to the request (k = 5 -> 8, k = 10 -> 12, k = 32 -> 32).
+int kcap_for(int k) {
+  if (const char* e = getenv("ZSAAC_KCAP_POW2")) {    // tuning hook: the former 8 / 16 / 32 only
+    if (e[0] == '1') return k <= 8 ? 8 : (k <= 16 ? 16 : 32);
+  }
+  return k <= 8 ? 8 : (k <= 12 ? 12 : (k <= 16 ? 16 : (k <= 24 ? 24 : 32)));
+}
 
 struct Plan {
   int cg, m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
@@ -311,7 +318,9 @@ int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkPara
                             : launch_simtopk<8, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st);
   switch (kcap_for(p.k)) {
     case 8: return launch_simtopk<8, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
+    case 12: return launch_simtopk<12, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
     case 16: return launch_simtopk<16, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
+    case 24: return launch_simtopk<24, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
     default: return launch_simtopk<32, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
   }
 }
