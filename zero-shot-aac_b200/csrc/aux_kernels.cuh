@@ -114,19 +114,14 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
   return a.src < b.src;
 }
 
-template <typename IdxT, int LPL>
-__global__ void __launch_bounds__(256)
-merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
-                   int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
-                   float* __restrict__ out_scores, long long* __restrict__ out_idx) {
-  ptx::pdl_wait();   // lists are written by the preceding grid (no-op without the PDL attribute)
-  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (q >= Q) return;
-
+// k-way merge of `n_lists` sorted lists by one warp: lane l owns lists l, l+32, ...; k rounds of a
+// warp arg-max over the list heads (xor butterfly on a strict total order, so every lane agrees).
+// load(list, pos, s, i) reads element `pos` of a list, store(r, s, i) receives result r (lane 0).
+// The successor of every head is fetched one round ahead, so a round never waits on a dependent
+// load.
+template <int LPL, typename Load, typename Store>
+__device__ __forceinline__ void warp_merge(int n_lists, int k, int lane, Load load, Store store) {
   const long long SENT = 0x7fffffffffffffffll;
-  // per owned list: position of the current head, the head itself and the element after it (the
-  // successor is fetched one round ahead, so the merge never waits on a dependent global load)
   int head[LPL];
   float hs[LPL], ns[LPL];
   long long hi[LPL], ni[LPL];
@@ -136,20 +131,13 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
     head[l] = 0;
     hs[l] = ns[l] = -CUDART_INF_F;
     hi[l] = ni[l] = SENT;
-    if (list < S) {
-      const int64_t so = static_cast<int64_t>(list) * score_stride + q * k;
-      const int64_t io = static_cast<int64_t>(list) * index_stride + q * k;
-      hs[l] = scores[so];
-      hi[l] = widen_index(idx[io]);
-      if (k > 1) {
-        ns[l] = scores[so + 1];
-        ni[l] = widen_index(idx[io + 1]);
-      }
+    if (list < n_lists) {
+      load(list, 0, hs[l], hi[l]);
+      if (k > 1) load(list, 1, ns[l], ni[l]);
     } else {
       head[l] = k;  // exhausted
     }
   }
-
   for (int r = 0; r < k; ++r) {
     Cand best{-CUDART_INF_F, SENT, 0x7fffffff};
 #pragma unroll
@@ -167,10 +155,7 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
       other.src = __shfl_xor_sync(0xffffffffu, best.src, o);
       if (cand_better(other, best)) best = other;
     }
-    if (lane == 0) {
-      out_scores[q * k + r] = best.s;
-      out_idx[q * k + r] = (best.i == SENT) ? -1ll : best.i + idx_offset;
-    }
+    if (lane == 0) store(r, best.s, best.i);
     // the owner of the winning list advances it: the prefetched successor becomes the head and
     // the element after that is requested
 #pragma unroll
@@ -179,13 +164,79 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
         ++head[l];
         hs[l] = ns[l];
         hi[l] = ni[l];
-        if (head[l] + 1 < k) {
-          const int64_t list = lane + 32 * l;
-          ns[l] = scores[list * score_stride + q * k + head[l] + 1];
-          ni[l] = widen_index(idx[list * index_stride + q * k + head[l] + 1]);
-        }
+        if (head[l] + 1 < k) load(lane + 32 * l, head[l] + 1, ns[l], ni[l]);
       }
     }
+  }
+}
+
+// One warp per query: enough parallelism whenever there are many queries.
+template <typename IdxT, int LPL>
+__global__ void __launch_bounds__(256)
+merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
+                   int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
+                   float* __restrict__ out_scores, long long* __restrict__ out_idx) {
+  ptx::pdl_wait();   // lists are written by the preceding grid (no-op without the PDL attribute)
+  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  const long long SENT = 0x7fffffffffffffffll;
+  warp_merge<LPL>(
+      S, k, lane,
+      [&](int list, int pos, float& s, long long& i) {
+        s = scores[static_cast<int64_t>(list) * score_stride + q * k + pos];
+        i = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k + pos]);
+      },
+      [&](int r, float s, long long i) {
+        out_scores[q * k + r] = s;
+        out_idx[q * k + r] = (i == SENT) ? -1ll : i + idx_offset;
+      });
+}
+
+// One block per query, for few queries with many lists (a small batch against a bank split into
+// a chunk per SM: up to 512 lists per query): the 8 warps each merge an eighth of the lists into
+// shared memory, warp 0 merges those 8.  ncu: 24 -> 12 us for 128 queries x 286 lists, 21 -> 11 us
+// for one query.
+constexpr int MERGE_BLOCK_WARPS = 8;
+constexpr int MERGE_BLOCK_MAX_K = 32;
+template <typename IdxT>
+__global__ void __launch_bounds__(32 * MERGE_BLOCK_WARPS)
+merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
+                         int64_t score_stride, int64_t index_stride, int64_t Q, int k,
+                         long long idx_offset, float* __restrict__ out_scores,
+                         long long* __restrict__ out_idx) {
+  __shared__ float part_s[MERGE_BLOCK_WARPS][MERGE_BLOCK_MAX_K];
+  __shared__ long long part_i[MERGE_BLOCK_WARPS][MERGE_BLOCK_MAX_K];
+  ptx::pdl_wait();
+  const int64_t q = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long SENT = 0x7fffffffffffffffll;
+  const int per_warp = (S + MERGE_BLOCK_WARPS - 1) / MERGE_BLOCK_WARPS;   // <= 64: two lists per lane
+  const int first = warp * per_warp;
+  const int mine = max(0, min(per_warp, S - first));
+  warp_merge<2>(
+      mine, k, lane,
+      [&](int list, int pos, float& s, long long& i) {
+        s = scores[static_cast<int64_t>(first + list) * score_stride + q * k + pos];
+        i = widen_index(idx[static_cast<int64_t>(first + list) * index_stride + q * k + pos]);
+      },
+      [&](int r, float s, long long i) {
+        part_s[warp][r] = s;
+        part_i[warp][r] = i;
+      });
+  __syncthreads();
+  if (warp == 0) {
+    warp_merge<1>(
+        MERGE_BLOCK_WARPS, k, lane,
+        [&](int list, int pos, float& s, long long& i) {
+          s = part_s[list][pos];
+          i = part_i[list][pos];
+        },
+        [&](int r, float s, long long i) {
+          out_scores[q * k + r] = s;
+          out_idx[q * k + r] = (i == SENT) ? -1ll : i + idx_offset;
+        });
   }
 }
 

@@ -256,6 +256,14 @@ cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t sc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  // few queries, many lists (a small batch against a bank split into a chunk per SM): a block per
+  // query instead of a warp per query
+  if (S > 64 && Q <= 4096 && k <= zs::MERGE_BLOCK_MAX_K) {
+    cfg.gridDim = dim3(static_cast<unsigned>(Q));
+    cfg.blockDim = dim3(32 * zs::MERGE_BLOCK_WARPS);
+    return cudaLaunchKernelEx(&cfg, zs::merge_lists_block_kernel<IdxT>, scores, idx, S, score_stride,
+                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+  }
   if (S <= 64)
     return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 2>, scores, idx, S, score_stride,
                               index_stride, Q, k, idx_offset, out_scores, out_idx);
