@@ -133,6 +133,22 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
              int64_t index_stride, int64_t Q, int k, float* out_scores, int64_t* out_indices,
              void* stream);
 
+/* fp32 re-scoring of search candidates: the fused kernel ranks with bf16-rounded operands, so
+ * bank rows whose scores differ by less than ~1e-4 may swap places against the reference's fp32
+ * `torch.cosine_similarity(text_embs, valid_text_embs).topk(topnumber)`
+ * (data_handing/embeddings_related_generator.py:22).  Search for kc = k + margin candidates,
+ * then call this with the caller's fp32 bank (the tensor load_data returned): every candidate is
+ * re-scored in fp32 — cosine with normalize != 0 (q.b / (max(|q|,1e-12) max(|b|,1e-12))), the raw
+ * dot product otherwise — and the k best under (score desc, index asc) are returned.
+ *   queries     [Q, d] fp32 (raw: normalisation happens here), bank [n_rows, d] fp32
+ *   candidates  [Q, kc] int64 global indices (index_offset = global index of bank row 0;
+ *               entries < 0 or outside the bank are ignored), kc <= 32
+ *   out_scores  [Q, k] fp32, out_indices [Q, k] int64 (-1 where fewer than k candidates exist)
+ * Stand-alone: needs no bf16 bank. */
+int zs_rescore_f32(zs_ctx* ctx, const float* queries, int64_t Q, int normalize, const float* bank,
+                   int64_t n_rows, int d, int64_t index_offset, const int64_t* candidates, int kc,
+                   int k, float* out_scores, int64_t* out_indices, void* stream);
+
 /* Gather rows: out[i, :] = src[indices[i], :] for fp32 [*, d] row-major src (replaces
  * `valid_text_embs[ids]`, reference embeddings_related_generator.py:23). */
 int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,

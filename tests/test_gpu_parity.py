@@ -267,6 +267,71 @@ def test_normalize_and_gather_kernels(zs):
     rb.close()
 
 
+# ------------------------------------------------------------------------ fp32 re-scoring
+@pytest.mark.parametrize("k", [1, 5, 10, 24, 32])
+def test_rescore_fp32_restores_the_fp32_ranking(zs, k):
+    """k + 8 bf16 candidates re-scored in fp32: scores are fp32 cosines (1e-6, not 1e-4), and the
+    index lists equal the fp32 oracle's except where the oracle itself is within 1e-6 of a tie.
+    (k = 32 leaves no margin: still exact scores, order as good as the candidates allow.)"""
+    q, b = helpers.seeded((600, 1024), 500 + k), helpers.clustered(30_000, 1024, 2048, 0.2, 501 + k)
+    s0, i0 = zs.related_topk(q.cuda(), b.cuda(), k)
+    s1, i1 = zs.related_topk(q.cuda(), b.cuda(), k, rescore_fp32=True)
+    torch.cuda.synchronize()
+    s0, i0, s1, i1 = s0.cpu(), i0.cpu(), s1.cpu(), i1.cpu()
+    full = oracle.exact_scores(q, b)                       # float64 cosines
+    ws, wi = oracle.stable_topk(torch.as_tensor(full, dtype=torch.float64), k)
+    at = torch.as_tensor(full).gather(1, i1)
+    assert (s1.double() - at).abs().max().item() < 2e-6
+    assert (s1[:, 1:] <= s1[:, :-1]).all()
+    rep = oracle.check_topk(s1, i1, q, b, k)
+    assert rep["ok"], rep
+    match1 = (i1 == wi).all(dim=1).float().mean().item()
+    match0 = (i0 == wi).all(dim=1).float().mean().item()
+    assert match1 >= match0
+    if k <= 24:
+        differs = (i1 != wi)
+        gap = (torch.as_tensor(full).gather(1, i1) - ws).abs()
+        assert (gap[differs] < 1e-6).all()                  # only fp32-level ties may differ
+
+
+def test_rescore_f32_standalone_edge_cases(zs):
+    """zs_rescore_f32 on hand-made candidate lists: ignored slots (-1, out of range), k == kc,
+    raw dot product, shard offset, ties broken by index."""
+    g = torch.Generator().manual_seed(77)
+    bank = torch.randn(400, 256, generator=g)
+    bank[11] = bank[7]                                      # exact tie
+    q = torch.randn(3, 256, generator=g)
+    rb = zs.RelatedBank(1, 256)                             # any context: the call needs no bf16 bank
+    cand = torch.tensor([[7, 11, -1, 399, 5000, 3], [0, 1, 2, 3, 4, 5], [11, 7, -1, -1, -1, 9]])
+    s, i = rb.rescore(q.cuda(), bank.cuda(), cand.cuda(), 4, normalize=True)
+    torch.cuda.synchronize()
+    s, i = s.cpu(), i.cpu()
+    cos = torch.nn.functional.normalize(q, dim=-1) @ torch.nn.functional.normalize(bank, dim=-1).T
+    for r in range(3):
+        valid = sorted({c for c in cand[r].tolist() if 0 <= c < 400}, key=lambda c: (-cos[r, c].item(), c))
+        want = (valid + [-1] * 4)[:4]
+        assert i[r].tolist() == want, (r, i[r].tolist(), want)
+        for slot, c in enumerate(want):
+            if c >= 0:
+                assert abs(s[r, slot].item() - cos[r, c].item()) < 1e-6
+            else:
+                assert s[r, slot].item() == float("-inf")
+    row0 = i[0].tolist()
+    assert row0.index(7) + 1 == row0.index(11)              # the twins tie exactly: lower index first
+    # raw dot product, k == kc, bank slice with a global offset
+    s2, i2 = rb.rescore(q.cuda(), bank[100:].cuda(), torch.tensor([[100, 101, 250]] * 3).cuda(), 3,
+                        normalize=False, index_offset=100)
+    torch.cuda.synchronize()
+    dots = q @ bank.T
+    for r in range(3):
+        want = sorted([100, 101, 250], key=lambda c: (-dots[r, c].item(), c))
+        assert i2[r].cpu().tolist() == want
+        assert torch.allclose(s2[r].cpu(), dots[r, want], atol=1e-4)
+    with pytest.raises(RuntimeError):
+        rb.rescore(q.cuda(), bank.cuda(), cand.cuda(), 7)   # k > kc
+    rb.close()
+
+
 # --------------------------------------------------------- full-size, size-independent properties
 def test_wavcaps_scale_properties(zs):
     """BASELINE config 3 size (8192 x 400k, k=10): checked through properties, not a full oracle."""

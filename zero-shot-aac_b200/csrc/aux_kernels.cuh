@@ -241,6 +241,77 @@ merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 re-scoring of the candidates the bf16 search returned (zs_rescore_f32).  The fused kernel
+// ranks with bf16-rounded operands (score error <= ~1e-4), so two bank rows closer than that can
+// swap places against the reference's fp32 torch.cosine_similarity(...).topk(k)
+// (embeddings_related_generator.py:22).  Searching for k + margin candidates and re-scoring them
+// from the caller's fp32 bank restores the fp32 ranking wherever the true top-k lies inside the
+// candidate set.
+//
+// One block (4 warps) per query: warps stride over the kc <= 32 candidates, each computes
+// q.b, q.q and b.b of one (query, candidate) pair in fp32 (16-byte loads, fixed summation order:
+// lane-strided, then xor butterfly) -> cosine = q.b / (max(|q|, eps) max(|b|, eps)), or the raw
+// q.b with normalize == 0; warp 0 then picks the k best under (score desc, index asc).
+constexpr int RESCORE_THREADS = 128;
+constexpr int RESCORE_MAX_CAND = 32;
+__global__ void __launch_bounds__(RESCORE_THREADS)
+rescore_f32_kernel(const float* __restrict__ queries, const float* __restrict__ bank, int64_t n_bank,
+                   int d, int normalize, const long long* __restrict__ cand, int kc, int k,
+                   long long idx_offset, float* __restrict__ out_scores,
+                   long long* __restrict__ out_idx) {
+  __shared__ float s_score[RESCORE_MAX_CAND];
+  __shared__ long long s_idx[RESCORE_MAX_CAND];
+  const int64_t q = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long SENT = 0x7fffffffffffffffll;
+  const float* qrow = queries + q * d;
+  for (int c = warp; c < kc; c += RESCORE_THREADS / 32) {
+    const long long g = cand[q * kc + c];
+    const long long col = g - idx_offset;
+    float score = -CUDART_INF_F;
+    long long keep = SENT;
+    if (g >= 0 && col >= 0 && col < n_bank) {          // (-1 marks an empty slot)
+      const float* brow = bank + col * d;
+      float qb = 0.f, qq = 0.f, bb = 0.f;
+      for (int e = lane * 4; e < d; e += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(qrow + e);
+        const float4 b = *reinterpret_cast<const float4*>(brow + e);
+        qb = fmaf(a.x, b.x, qb); qb = fmaf(a.y, b.y, qb); qb = fmaf(a.z, b.z, qb); qb = fmaf(a.w, b.w, qb);
+        qq = fmaf(a.x, a.x, qq); qq = fmaf(a.y, a.y, qq); qq = fmaf(a.z, a.z, qq); qq = fmaf(a.w, a.w, qq);
+        bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
+      }
+      qb = warp_sum(qb); qq = warp_sum(qq); bb = warp_sum(bb);
+      score = normalize ? qb / (fmaxf(sqrtf(qq), 1e-12f) * fmaxf(sqrtf(bb), 1e-12f)) : qb;
+      if (score != score) score = -CUDART_INF_F;       // NaN never ranks (as in the search)
+      keep = g;
+    }
+    if (lane == 0) { s_score[c] = score; s_idx[c] = keep; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    Cand mine{-CUDART_INF_F, SENT, lane};
+    if (lane < kc) { mine.s = s_score[lane]; mine.i = s_idx[lane]; }
+    for (int r = 0; r < k; ++r) {
+      Cand best = mine;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Cand other;
+        other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
+        other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+        other.src = __shfl_xor_sync(0xffffffffu, best.src, o);
+        if (cand_better(other, best)) best = other;
+      }
+      if (lane == 0) {
+        out_scores[q * k + r] = best.s;
+        out_idx[q * k + r] = (best.i == SENT) ? -1ll : best.i;
+      }
+      if (best.src == lane) { mine.s = -CUDART_INF_F; mine.i = SENT; mine.src = 64 + lane; }  // taken
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Rank-of-target support (retrieval metrics a2t / t2a, reference retrieval/tools/utils.py:169-251)
 
 // One warp per (query, target): score = <bf16 query row, bf16 bank row> in fp32, i.e. the same

@@ -744,6 +744,31 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
   return ZS_OK;
 }
 
+int zs_rescore_f32(zs_ctx* ctx, const float* queries, int64_t Q, int normalize, const float* bank,
+                   int64_t n_rows, int d, int64_t index_offset, const int64_t* candidates, int kc,
+                   int k, float* out_scores, int64_t* out_indices, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_rescore_f32: ctx is null");
+  if (Q < 0 || n_rows < 1) return fail(ZS_ERR_INVALID, "zs_rescore_f32: Q=%lld n_rows=%lld",
+                                       (long long)Q, (long long)n_rows);
+  if (d < 4 || d % 4 != 0) return fail(ZS_ERR_INVALID, "zs_rescore_f32: d=%d must be a multiple of 4", d);
+  if (kc < 1 || kc > zs::RESCORE_MAX_CAND || k < 1 || k > kc)
+    return fail(ZS_ERR_INVALID, "zs_rescore_f32: need 1 <= k <= kc <= %d (k=%d, kc=%d)",
+                zs::RESCORE_MAX_CAND, k, kc);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !bank || !candidates || !out_scores || !out_indices)
+    return fail(ZS_ERR_INVALID, "zs_rescore_f32: null pointer");
+  if (!aligned16(queries) || !aligned16(bank))
+    return fail(ZS_ERR_INVALID, "zs_rescore_f32: queries and bank must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  zs::rescore_f32_kernel<<<static_cast<unsigned>(Q), zs::RESCORE_THREADS, 0, st>>>(
+      queries, bank, n_rows, d, normalize, reinterpret_cast<const long long*>(candidates), kc, k,
+      index_offset, out_scores, reinterpret_cast<long long*>(out_indices));
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
 int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,
                        const int64_t* indices, int64_t n_idx, float* out, void* stream) {
   if (!ctx) return fail(ZS_ERR_INVALID, "zs_gather_rows_f32: ctx is null");

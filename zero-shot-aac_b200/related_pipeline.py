@@ -17,7 +17,7 @@ from typing import Iterable, Iterator, List, Sequence, Tuple, Union
 
 import torch
 
-from .retrieval import RelatedBank, _require_cuda, bank_for
+from .retrieval import RelatedBank, _require_cuda, bank_for, search_rescored
 
 try:  # the reference wraps the writer loop in tqdm (embeddings_related_generator.py:33)
     from tqdm import tqdm
@@ -73,7 +73,7 @@ def _register_bank(bank: torch.Tensor, rb: RelatedBank) -> None:
 
 
 def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnumber: int,
-                 *, exclude_self: bool = False) -> Iterator[dict]:
+                 *, exclude_self: bool = False, rescore_fp32: bool = True) -> Iterator[dict]:
     """Yield every item with `related_embeddings` = its top-`topnumber` bank rows, best first.
 
     Reference: embeddings_related_generator.py:19-28.  valid_text_embs is the fp32 bank returned
@@ -82,6 +82,9 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
     valid_text_embs itself (:23): exact copies of the caller's bank rows, whatever precision the
     search ran in.  item['text_embedding'] is moved to the CPU (:25).  Like the reference there is no
     self-exclusion unless exclude_self=True (opt-in; assumes item i is bank row i).
+    rescore_fp32 (default on): the fused kernel ranks bf16-rounded operands; its k + 8 best
+    candidates are re-scored in fp32 from valid_text_embs, so the k rows kept are the reference's
+    fp32 choice also where two captions are closer than the bf16 resolution (~1e-4).
     """
     _require_cuda()
     if not valid_text_embs.is_cuda:
@@ -101,7 +104,11 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
         self_index = None
         if exclude_self:
             self_index = torch.arange(first, first + len(items), dtype=torch.int64, device=device)
-        _, ids = rb.search(q_dev, topnumber, normalize_queries=True, self_index=self_index)
+        if rescore_fp32:
+            _, ids = search_rescored(rb, q_dev, valid_text_embs, topnumber, normalize=True,
+                                     self_index=self_index)
+        else:
+            _, ids = rb.search(q_dev, topnumber, normalize_queries=True, self_index=self_index)
         related = rb.gather_rows(valid_text_embs, ids)                 # [B, k, d] fp32 on the GPU
         related_host = torch.empty(related.shape, dtype=torch.float32).pin_memory()
         related_host.copy_(related, non_blocking=True)

@@ -169,6 +169,40 @@ class RelatedBank:
                 _stream_ptr(self.device)))
         return ranks, scores
 
+    def rescore(self, queries: torch.Tensor, bank_f32: torch.Tensor, candidates: torch.Tensor, k: int,
+                *, normalize: bool = True, index_offset: int = 0
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Re-score search candidates in fp32 and keep the k best (score desc, index asc).
+
+        queries [Q, d] float32 (raw), bank_f32 [N, d] float32 on this device, candidates [Q, kc]
+        int64 global indices (kc <= 32; bank_f32 row 0 has global index `index_offset`).  With
+        normalize=True the score is the cosine similarity computed entirely in fp32 — the
+        arithmetic of the reference's torch.cosine_similarity (embeddings_related_generator.py:22)
+        — so searching for k + margin candidates and re-scoring them removes the bf16 near-tie
+        swaps of the fused kernel.
+        """
+        if queries.dtype != torch.float32 or bank_f32.dtype != torch.float32:
+            raise TypeError("rescore expects float32 queries and a float32 bank")
+        if queries.dim() != 2 or bank_f32.dim() != 2 or queries.shape[1] != bank_f32.shape[1]:
+            raise ValueError("rescore expects queries [Q, d] and bank [N, d]")
+        if queries.device != self.device or bank_f32.device != self.device:
+            raise ValueError(f"rescore expects tensors on {self.device}")
+        queries = queries.detach().contiguous()
+        bank_f32 = bank_f32.detach().contiguous()
+        cand = candidates.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        q = queries.shape[0]
+        if cand.dim() != 2 or cand.shape[0] != q:
+            raise ValueError(f"candidates must be [{q}, kc], got {tuple(cand.shape)}")
+        kc, k = cand.shape[1], int(k)
+        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.zs_rescore_f32(
+                self._ctx, queries.data_ptr(), q, 1 if normalize else 0, bank_f32.data_ptr(),
+                bank_f32.shape[0], bank_f32.shape[1], int(index_offset), cand.data_ptr(), kc, k,
+                out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(self.device)))
+        return out_s, out_i
+
     def debug_scores(self, queries: torch.Tensor, *, normalize_queries: bool = True) -> torch.Tensor:
         """Full [Q, rows] similarity matrix out of the same tcgen05 pipeline (tests only)."""
         queries = queries.detach().contiguous()
@@ -297,9 +331,12 @@ def clear_bank_cache() -> None:
         _BANK_CACHE.popitem()[1][1].close()
 
 
+RESCORE_MARGIN = 8      # extra candidates fetched for fp32 re-scoring (k + margin <= 32)
+
+
 def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_self: bool = False,
-                 self_index: Optional[torch.Tensor] = None, normalize: bool = True
-                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+                 self_index: Optional[torch.Tensor] = None, normalize: bool = True,
+                 rescore_fp32: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """scores, indices = top-k of cosine_similarity(queries, bank).
 
     queries [Q, d], bank [N, d] (float32 or bfloat16).  With normalize=True both sides are
@@ -307,6 +344,7 @@ def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_s
     with normalize=False the raw dot product is ranked (reference utils.py:133).
     exclude_self=True drops bank row i from the result of query i (self_index defaults to
     arange(Q)); the reference itself never excludes (slot 0 of its output is the item).
+    rescore_fp32=True re-scores k + 8 bf16 candidates in fp32 from `bank` (float32 inputs only).
     Returns float32 [Q, k] scores (descending) and int64 [Q, k] bank indices on the GPU.
     """
     _require_cuda()
@@ -317,4 +355,21 @@ def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_s
     q = q.to(rb.device)
     if exclude_self and self_index is None:
         self_index = torch.arange(q.shape[0], dtype=torch.int64, device=rb.device)
-    return rb.search(q, k, normalize_queries=normalize, self_index=self_index)
+    if not rescore_fp32:
+        return rb.search(q, k, normalize_queries=normalize, self_index=self_index)
+    return search_rescored(rb, q, bank, k, normalize=normalize, self_index=self_index)
+
+
+def search_rescored(rb: RelatedBank, queries: torch.Tensor, bank_f32: torch.Tensor, k: int, *,
+                    normalize: bool = True, self_index: Optional[torch.Tensor] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16 search for k + RESCORE_MARGIN candidates, then fp32 re-scoring from `bank_f32` (the
+    float32 tensor the bf16 bank `rb` was built from) down to k: scores and order are those of an
+    fp32 cosine similarity wherever the true top-k lies inside the candidate set."""
+    if bank_f32.dtype != torch.float32 or queries.dtype != torch.float32:
+        raise TypeError("rescore_fp32 needs float32 queries and a float32 bank")
+    bank_dev = bank_f32 if bank_f32.device == rb.device else bank_f32.to(rb.device)
+    avail = rb.rows - (1 if self_index is not None else 0)
+    kc = max(int(k), min(int(k) + RESCORE_MARGIN, _abi.ZS_MAX_K, avail))
+    _, cand = rb.search(queries, kc, normalize_queries=normalize, self_index=self_index)
+    return rb.rescore(queries, bank_dev, cand, k, normalize=normalize, index_offset=rb.index_offset)
