@@ -1,0 +1,90 @@
+"""Randomised stress of the fused search against a torch restatement on the same GPU (run under
+gpurun).  Every case draws Q, N, k, forced chunk count, CTA-group, self-exclusion, normalisation,
+input dtype and a shard offset; the expectation multiplies the SAME bf16-rounded operands in fp32
+(torch.matmul) and ranks under (score desc, index asc), so indices must agree wherever the
+expected scores are not within 1e-5 (relative to the row's largest |score|) of each other
+(accumulation order), and scores within the same bound.
+usage: python tools/stress_random.py [cases] [seed]"""
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rng = random.Random(seed)
+dev = torch.device("cuda", 0)
+bad = 0
+for case in range(n_cases):
+    cg = rng.choice(["1", "2", "auto"])
+    if cg == "auto":
+        os.environ.pop("ZSAAC_CTA_GROUP", None)
+    else:
+        os.environ["ZSAAC_CTA_GROUP"] = cg
+    import zsaac_b200
+    N = rng.choice([rng.randint(1, 600), rng.randint(600, 20_000), rng.randint(20_000, 120_000)])
+    Q = rng.choice([rng.randint(1, 40), rng.randint(40, 700), rng.randint(700, 3000)])
+    d = rng.choice([64, 128, 256, 1024, 1024, 1024])
+    excl = rng.random() < 0.3 and N > 1
+    k = rng.randint(1, min(32, N - (1 if excl else 0)))
+    normalize = rng.random() < 0.7
+    bf16_in = rng.random() < 0.25
+    offset = rng.choice([0, 0, 12345, 10 ** 9])
+    chunks = rng.choice([0, 0, rng.randint(1, 256)])
+    if chunks:
+        os.environ["ZSAAC_CHUNKS"] = str(chunks)
+    else:
+        os.environ.pop("ZSAAC_CHUNKS", None)
+    g = torch.Generator(device=dev).manual_seed(seed * 100003 + case)
+    kind = rng.choice(["gauss", "clustered", "dups"])
+    b = torch.randn(N, d, device=dev, generator=g)
+    if kind == "clustered" and N > 64:
+        centres = torch.randn(32, d, device=dev, generator=g)
+        b = centres[torch.randint(0, 32, (N,), device=dev, generator=g)] + 0.05 * b
+    if kind == "dups" and N > 8:
+        b[N // 2:] = b[: N - N // 2].clone()                           # exact duplicates: ties by index
+    q = torch.randn(Q, d, device=dev, generator=g)
+    if bf16_in:
+        b, q = b.bfloat16(), q.bfloat16()
+    self_index = None
+    if excl:
+        self_index = torch.randint(0, N, (Q,), device=dev, generator=g) + offset
+    rb = zsaac_b200.RelatedBank.from_tensor(b, normalize=normalize, index_offset=offset)
+    s, i = rb.search(q, k, normalize_queries=normalize, self_index=self_index)
+    # expectation from the same bf16 operands (the library's own fp32 normalise)
+    qf, bf = q.float(), b.float()
+    if normalize:
+        qf, bf = rb.normalize_rows(qf), rb.normalize_rows(bf)
+    full = qf.bfloat16().float() @ bf.bfloat16().float().T
+    if excl:
+        full[torch.arange(Q, device=dev), self_index - offset] = -float("inf")
+    order = torch.sort(full, dim=1, descending=True, stable=True)
+    ws, wi = order.values[:, :k], order.indices[:, :k] + offset
+    torch.cuda.synchronize()
+    # fp32 accumulation in the tensor core vs in cuBLAS' FMA chain: the difference scales with the
+    # magnitude of the partial sums, i.e. with the largest |score| of the row (measured up
+    # to 4.5e-6 relative on unnormalised rows, 1e-7 on unit rows)
+    finite = torch.where(torch.isfinite(full), full, torch.zeros_like(full))
+    tol = 1e-5 * (1 + finite.abs().max(dim=1, keepdim=True).values)
+    ok_s = bool(((s - ws).abs() <= tol).all())
+    got_ref = full.gather(1, i - offset)
+    ok_i = bool(((i == wi) | ((got_ref - ws).abs() <= tol)).all())
+    ok_sorted = bool((s[:, 1:] <= s[:, :-1]).all())
+    ok_distinct = k == 1 or bool((torch.sort(i, dim=1).values.diff(dim=1) != 0).all())
+    ok = ok_s and ok_i and ok_sorted and ok_distinct
+    if not ok:
+        bad += 1
+    if not ok_s:
+        rel = ((s - ws).abs() / (1 + finite.abs().max(dim=1, keepdim=True).values)).max().item()
+        print(f"   worst |score - expected| relative to the row's largest |score|: {rel:.2e}")
+    if not ok or case % 25 == 0:
+        print(f"case {case}: Q={Q} N={N} d={d} k={k} cg={cg} chunks={chunks} plan={rb.plan(Q, k)} "
+              f"excl={excl} norm={normalize} bf16={bf16_in} off={offset} {kind} -> "
+              f"{'ok' if ok else 'MISMATCH'} (scores {ok_s}, indices {ok_i}, sorted {ok_sorted}, "
+              f"distinct {ok_distinct})", flush=True)
+    rb.close()
+    del rb, b, q, full
+print(f"stress: {n_cases - bad}/{n_cases} cases ok (seed {seed})")
+sys.exit(1 if bad else 0)
