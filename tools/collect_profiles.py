@@ -64,13 +64,16 @@ traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 rep = os.path.join(SRC, "prof_simtopk.ncu-rep")
 if os.path.exists(rep):
     traffic["wavcaps_400k"] = summarise_full(rep, "wavcaps_400k")
+rep = os.path.join(SRC, "prof_simtopk_default.ncu-rep")      # --set full of the default workload
+if os.path.exists(rep):
+    traffic["synthetic_10m"] = summarise_full(rep, "synthetic_10m")
 dram = os.path.join(SRC, "ncu_dram_default.csv")
 if os.path.exists(dram):
     vals = {}
     for r in csv.reader(open(dram)):
         if len(r) > 3 and r[-3].startswith("dram__bytes"):
             vals[r[-3]] = float(r[-1].replace(",", ""))
-    if vals:
+    if vals and "synthetic_10m" not in traffic:
         traffic["synthetic_10m"] = sum(vals.values())
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 print(json.dumps({k: v for k, v in traffic.items() if not k.startswith("_")}))
