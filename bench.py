@@ -38,6 +38,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "synthetic_10m"
 BANK_BLOCK = 65536          # rows per generation block; seed = bank_seed * 2**32 + block id
 L2_BYTES = 126 << 20        # B200 L2 capacity
+REBALANCE_DEFAULT = False
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -250,6 +251,39 @@ def run_ours(args):
         lo, hi = 0, N
     fill_shard(torch, local, lo, hi, bank_seed, device)
 
+    # ---- N > 1: size the shards by the measured speed of each GPU (untimed calibration).  Every
+    # step ends in an all-gather, so the slowest GPU sets the pace, and the GPUs of one box differ
+    # by several per cent under the power cap (kernel_ms_per_rank).  Two calibration searches on
+    # equal shards give rows/ms per rank; if the ranks differ by more than 2 % the bank is
+    # re-sharded in proportion (ShardedRelatedBank(shard_weights=...)) and refilled.
+    shard_weights = None
+    if world > 1 and args.rebalance:
+        qc = gen_queries(torch, Q, q_seed).to(device)
+        local.reserve(Q, k)
+        for _ in range(2):
+            bank.search(qc, k)
+        torch.cuda.synchronize(device)
+        local.profile(True)
+        for _ in range(2):
+            bank.search(qc, k)
+        torch.cuda.synchronize(device)
+        t_cal = statistics.mean(local.kernel_times_ms())
+        local.profile(False)
+        speeds = torch.zeros(world, device=device, dtype=torch.float64)
+        speeds[rank] = (hi - lo) / t_cal
+        dist.all_reduce(speeds, op=dist.ReduceOp.SUM)
+        speeds = speeds.tolist()
+        if max(speeds) / min(speeds) > 1.02:
+            shard_weights = [round(v / max(speeds), 4) for v in speeds]
+            local.close()
+            del bank, local
+            torch.cuda.empty_cache()
+            bank = ShardedRelatedBank(N, D, device=device, shard_weights=shard_weights)
+            lo, hi = bank.lo, bank.hi
+            local = bank.local
+            fill_shard(torch, local, lo, hi, bank_seed, device)
+        del qc
+
     if excl:
         # BASELINE config 5: queries are the bank rows themselves after the reference's
         # noise_injection (utils.py:19-31: normalise, add N(0, 0.001 I), renormalise in search)
@@ -272,7 +306,9 @@ def run_ours(args):
         return bank.search(q_dev, k, self_index=self_index)
 
     def step_e2e():
-        qd = q_host.to(device, non_blocking=True)
+        # N > 1: every rank uploads 1/N of the host batch and the slices are all-gathered over
+        # NVLink (ShardedRelatedBank.replicate_from_host) instead of N full PCIe copies
+        qd = bank.replicate_from_host(q_host) if world > 1 else q_host.to(device, non_blocking=True)
         s, i = bank.search(qd, k, self_index=self_index)
         out_host_s.copy_(s, non_blocking=True)
         out_host_i.copy_(i, non_blocking=True)
@@ -396,7 +432,8 @@ def run_ours(args):
                             + (", self-exclusion" if excl else ""),
                 "parallelism": f"bank row-sharded over {world} GPU(s), queries replicated, "
                                "all-gather + k-way merge" if world > 1 else "single GPU",
-                "bank_rows_per_gpu": shard_rows, "bank_dtype": "bf16", "accumulate": "fp32",
+                "bank_rows_per_gpu": shard_rows, "shard_weights": shard_weights,
+                "bank_dtype": "bf16", "accumulate": "fp32",
                 "l2": ("L2 flushed between timed steps (256 MB write); bank shard %.0f MB + queries "
                        "%.0f MB per step" % (shard_rows * D * 2 / 1e6, Q * D * 4 / 1e6)) if flush_l2
                       else ("inputs larger than L2: bank shard %.1f GB + queries %.0f MB per step"
@@ -407,7 +444,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": world * Q * D * 4, "d2h_bytes_per_step": world * Q * k * 12},
+                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": world * Q * k * 12},
             "gpu_launches": int(launches) * world,
             "clocks": clock_report,
         }
@@ -428,6 +465,8 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override the query count (smoke runs)")
     ap.add_argument("--bank-rows", type=int, default=0, help="override the bank rows (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rebalance", action=argparse.BooleanOptionalAction, default=REBALANCE_DEFAULT,
+                    help="N > 1: size the bank shards by the measured speed of each GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -113,6 +113,26 @@ def test_shard_bounds_cover_the_bank_exactly():
     assert shard_bounds(10_000_000, 8)[3] == (3_750_000, 5_000_000)
 
 
+def test_weighted_shard_bounds():
+    from zsaac_b200.sharded import SHARD_ALIGN, shard_bounds
+    for n, w in [(10_000_000, [1.0, 0.97, 1.02, 1.0, 0.93, 1.01, 0.99, 1.04]), (1000, [1, 1, 1, 5]),
+                 (300, [1, 1]), (5, [3, 1, 1, 1]), (70_000, [1e-3, 1.0])]:
+        b = shard_bounds(n, len(w), w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[r][1] == b[r + 1][0] for r in range(len(w) - 1))
+        assert all(lo <= hi for lo, hi in b)
+        if n == 10_000_000:                                        # large banks: cuts on tile boundaries
+            assert all(lo % SHARD_ALIGN == 0 for lo, _ in b[1:])
+        if n >= len(w):
+            assert all(hi > lo for lo, hi in b)                    # nobody is left without rows
+    b = shard_bounds(10_000_000, 2, [3.0, 1.0])
+    assert abs((b[0][1] - b[0][0]) - 7_500_000) <= SHARD_ALIGN
+    assert shard_bounds(1000, 4, None) == shard_bounds(1000, 4)
+    for bad in ([1.0], [1.0, 0.0], [1.0, -1.0], [1.0, float("nan")]):
+        with pytest.raises(ValueError):
+            shard_bounds(100, 2, bad)
+
+
 def test_parallel_writer_emits_the_same_bytes_as_the_serial_loop(tmp_path, monkeypatch):
     """save_data_to_hdf5(workers=N) must write exactly the reference's per-record pickle stream."""
     import pickle

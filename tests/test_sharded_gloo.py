@@ -76,8 +76,17 @@ def _worker(rank, world, port, n_rows, k, exclude_self, result_dir):
         assert torch.equal(s, ws)
         if not exclude_self:
             assert i[0, :2].tolist() == [5, n_rows // 2 + 3]      # tie: ascending global index
+        # every rank uploads a slice of the host batch, the slices are all-gathered
+        for n_q in (37, 2, 1):
+            assert torch.equal(sb.replicate_from_host(queries[:n_q]), queries[:n_q])
         with pytest.raises(RuntimeError, match="out of range"):
             sb.search(queries, n_rows)                              # k larger than a shard
+        # shards sized by (made-up) GPU speeds: same global answer
+        sw = ShardedRelatedBank(n_rows, 128, local_bank_factory=OracleBank, shard_weights=[1.0, 2.5])
+        assert sw.bounds[0][1] == sw.bounds[1][0] and sw.bounds[0][1] - sw.bounds[0][0] < n_rows // 2
+        sw.upload_global(bank)
+        s2, i2 = sw.search(queries, k, self_index=self_index)
+        assert torch.equal(i2, wi) and torch.equal(s2, ws)
         torch.save((s, i), os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
