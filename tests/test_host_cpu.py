@@ -155,3 +155,40 @@ def test_parallel_writer_emits_the_same_bytes_as_the_serial_loop(tmp_path, monke
                 break
     assert len(back) == 153 and torch.equal(back[-1]["related_embeddings"], items[2]["related_embeddings"])
     assert not list(tmp_path.glob("*.part*"))
+
+
+def test_fast_pickle_stream_loads_to_the_same_records(tmp_path, monkeypatch):
+    """save_data_to_hdf5(fast_pickle=True): different bytes, but the reference's reader loop
+    (dataset/dataset.py:64-78, restated in helpers.read_related_stream) gets the same dicts of
+    torch tensors — dtype, shape, values, writable — serially and from the parallel writer."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from zsaac_b200 import related_pipeline as rp
+    monkeypatch.setattr(rp, "WRITER_BATCH", 41)
+    g = torch.Generator().manual_seed(4)
+    items = [{"caption": f"caption {i}", "text_id": i, "audio_id": f"a{i}.wav",
+              "text_embedding": torch.randn(1, 64, generator=g),
+              "related_embeddings": torch.randn(5, 64, generator=g),
+              "half": torch.randn(3, generator=g).bfloat16(),          # no numpy dtype: torch's own path
+              "view": torch.randn(4, 8, generator=g)[:, ::2]}          # non-contiguous
+             for i in range(120)]
+    plain, fast, fast_par = tmp_path / "plain.pkl", tmp_path / "fast.pkl", tmp_path / "fast_par.pkl"
+    rp.save_data_to_hdf5(iter(items), str(plain), len(items))
+    rp.save_data_to_hdf5(iter(items), str(fast), len(items), fast_pickle=True)
+    rp.save_data_to_hdf5(iter(items), str(fast_par), len(items), workers=3, fast_pickle=True)
+    assert fast.read_bytes() == fast_par.read_bytes() and fast.read_bytes() != plain.read_bytes()
+    want = helpers.read_related_stream(str(plain))
+    for path in (fast, fast_par):
+        got = helpers.read_related_stream(str(path))
+        assert len(got) == len(want) == 120
+        for a, b in zip(got, want):
+            assert a.keys() == b.keys() and a["caption"] == b["caption"] and a["text_id"] == b["text_id"]
+            for key in ("text_embedding", "related_embeddings", "half", "view"):
+                assert type(a[key]) is torch.Tensor and a[key].dtype == b[key].dtype
+                assert a[key].shape == b[key].shape and torch.equal(a[key], b[key])
+                assert not a[key].requires_grad
+        got[0]["related_embeddings"][0, 0] = 1.0                             # writable
+    monkeypatch.setenv("ZSAAC_FAST_PICKLE", "1")                             # env default
+    env_path = tmp_path / "env.pkl"
+    rp.save_data_to_hdf5(iter(items), str(env_path), len(items))
+    assert env_path.read_bytes() == fast.read_bytes()

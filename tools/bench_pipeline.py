@@ -66,6 +66,37 @@ def main():
                 "parallel_output_identical": os.path.getsize(dst) == os.path.getsize(dst2)
                 and open(dst, "rb").read(1 << 24) == open(dst2, "rb").read(1 << 24)})
     os.remove(dst2)
+    # opt-in numpy-backed tensor pickling (same records after pickle.load, different bytes), and
+    # what the reference's reader loop (dataset/dataset.py:64-78) pays for either file
+    dst3 = os.path.join(tmp, "out_related_fast.pkl")
+    t8 = time.perf_counter()
+    gen.save_data_to_hdf5(iter(items), dst3, len(items), fast_pickle=True)
+    t9 = time.perf_counter()
+
+    def read_stream(path, limit):
+        got = []
+        with open(path, "rb") as f:
+            while len(got) < limit:
+                try:
+                    got.append(pickle.load(f))
+                except EOFError:
+                    break
+        return got
+
+    t10 = time.perf_counter()
+    back_plain = read_stream(dst, 10000)
+    t11 = time.perf_counter()
+    back_fast = read_stream(dst3, 10000)
+    t12 = time.perf_counter()
+    out.update({"save_fast_pickle_s": round(t9 - t8, 3),
+                "read_back_10000_records_s": round(t11 - t10, 3),
+                "read_back_10000_records_fast_pickle_s": round(t12 - t11, 3),
+                "fast_pickle_records_equal": all(
+                    torch.equal(a["related_embeddings"], b["related_embeddings"])
+                    and torch.equal(a["text_embedding"], b["text_embedding"]) and a["caption"] == b["caption"]
+                    for a, b in zip(back_plain, back_fast))})
+    del back_plain, back_fast
+    os.remove(dst3)
 
     # the search itself (what the kernel work amounts to inside process_data)
     rb = zsaac_b200.retrieval.bank_for(bank, normalize=True)

@@ -26,11 +26,14 @@ def main(argv=None):
     parser.add_argument('--topnumber', type=int, default=5)
     # extension (not in the reference): pickle the output records in N forked processes
     parser.add_argument('--writer_procs', type=int, default=None)
+    # extension: pickle tensors through numpy (same objects after pickle.load, ~3x faster)
+    parser.add_argument('--fast_pickle', action='store_true', default=None)
     args = parser.parse_args(argv)
     valid_text_embs, all_data = load_data(args.input_path)
     processed_data_gen = process_data(valid_text_embs, all_data, args.topnumber)
     total_items = len(all_data)
-    save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs)
+    save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs,
+                      fast_pickle=args.fast_pickle)
 
 
 if __name__ == '__main__':

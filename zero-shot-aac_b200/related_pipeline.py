@@ -132,6 +132,33 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
 # records pickled per parallel round of the optional multi-process writer
 WRITER_BATCH = 8192
 _WRITER_ITEMS: List[dict] = []      # read by forked writer processes (copy-on-write, never sent)
+_WRITER_FAST = False
+
+_NUMPY_DTYPES = (torch.float32, torch.float64, torch.float16, torch.int64, torch.int32, torch.int16,
+                 torch.int8, torch.uint8, torch.bool)
+
+
+class _FastTensorPickler(pickle.Pickler):
+    """Opt-in record writer: plain CPU tensors are pickled as `torch.from_numpy(ndarray)` instead
+    of torch's own reduction (which runs torch.save on every storage: ~100 us per tensor).  The
+    stream is still one pickle per record and `pickle.load` still returns the same dicts of
+    torch.Tensor (same dtype / shape / values, writable) — the reference's reader
+    (dataset/dataset.py:64-78) needs no change and reads such a file ~4x faster too — but the
+    bytes on disk are not the ones torch's reduction would have produced, hence opt-in."""
+
+    def reducer_override(self, obj):
+        if (isinstance(obj, torch.Tensor) and type(obj) is torch.Tensor and obj.device.type == "cpu"
+                and obj.layout == torch.strided and not obj.requires_grad
+                and obj.dtype in _NUMPY_DTYPES):
+            return (torch.from_numpy, (obj.detach().numpy(),))
+        return NotImplemented
+
+
+def _dump_record(item: dict, file, fast: bool) -> None:
+    if fast:
+        _FastTensorPickler(file, protocol=pickle.DEFAULT_PROTOCOL).dump(item)
+    else:
+        pickle.dump(item, file)                          # reference :34
 
 
 def _pickle_slice(args) -> str:
@@ -139,19 +166,21 @@ def _pickle_slice(args) -> str:
     lo, hi, part_path = args
     with open(part_path, "wb") as f:
         for item in _WRITER_ITEMS[lo:hi]:
-            pickle.dump(item, f)
+            _dump_record(item, f, _WRITER_FAST)
     return part_path
 
 
-def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str) -> None:
+def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str,
+                          fast: bool = False) -> None:
     """Pickle `items` in `workers` forked processes (pickling tensors is GIL-bound Python, ~80 us
     per record) and append the parts to `file` in order.  The bytes are exactly what the serial
     loop would have written."""
     import multiprocessing as mp
     import os
     import shutil
-    global _WRITER_ITEMS
+    global _WRITER_ITEMS, _WRITER_FAST
     _WRITER_ITEMS = items
+    _WRITER_FAST = fast
     n = len(items)
     per = -(-n // workers)
     jobs = [(lo, min(lo + per, n), f"{tmp_prefix}.part{j}") for j, lo in enumerate(range(0, n, per))]
@@ -170,30 +199,35 @@ def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str
 
 
 def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, total_items: int,
-                      *, workers: int = None) -> None:
+                      *, workers: int = None, fast_pickle: bool = None) -> None:
     """Append one pickle per record to output_path (reference :30-34; the name is historical —
     the format is a pickle stream, read back by dataset/dataset.py:64-78).
 
     workers (default: env ZSAAC_WRITER_PROCS, else 0): 0 reproduces the reference's serial loop;
     N > 0 pickles batches of records in N forked processes — same bytes, same order — because
-    once the search takes milliseconds the per-record pickling dominates the script."""
+    once the search takes milliseconds the per-record pickling dominates the script.
+    fast_pickle (default: env ZSAAC_FAST_PICKLE=1, else off): pickle tensors through numpy
+    (_FastTensorPickler): ~3x faster to write and ~4x faster to read back, same objects after
+    pickle.load, different bytes on disk."""
     import os
     if workers is None:
         workers = int(os.environ.get("ZSAAC_WRITER_PROCS", "0"))
+    if fast_pickle is None:
+        fast_pickle = os.environ.get("ZSAAC_FAST_PICKLE", "0") == "1"
     with open(output_path, "ab") as file:
         if workers <= 0:
             for i, item in enumerate(tqdm(processed_data_gen, total=total_items)):
-                pickle.dump(item, file)
+                _dump_record(item, file, fast_pickle)
             return
         batch: List[dict] = []
         progress = tqdm(total=total_items)
         for item in processed_data_gen:
             batch.append(item)
             if len(batch) == WRITER_BATCH:
-                _write_batch_parallel(batch, file, workers, output_path)
+                _write_batch_parallel(batch, file, workers, output_path, fast_pickle)
                 progress.update(len(batch))
                 batch = []
         if batch:
-            _write_batch_parallel(batch, file, workers, output_path)
+            _write_batch_parallel(batch, file, workers, output_path, fast_pickle)
             progress.update(len(batch))
         progress.close()
