@@ -192,3 +192,54 @@ def test_fast_pickle_stream_loads_to_the_same_records(tmp_path, monkeypatch):
     env_path = tmp_path / "env.pkl"
     rp.save_data_to_hdf5(iter(items), str(env_path), len(items))
     assert env_path.read_bytes() == fast.read_bytes()
+
+
+def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
+    """_read_records resolves torch's per-tensor `_load_from_bytes` to a direct parser of the legacy
+    storage stream; the records must equal pickle.load's in every dtype / view / edge case, and
+    anything it does not recognise must go through torch's own loader."""
+    import pickle
+    from zsaac_b200 import related_pipeline as rp
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(6, 8, generator=g)
+    recs = [{"caption": f"c{i}", "text_id": i, "text_embedding": torch.randn(1, 64, generator=g),
+             "view": base[:, ::2], "row": base[3], "long": torch.arange(5) * i,
+             "half": torch.randn(3, generator=g).half(), "bf16": torch.randn(3, generator=g).bfloat16(),
+             "bool": torch.tensor([True, False]), "empty": torch.empty(0), "scalar": torch.tensor(2.5),
+             "f64": torch.randn(2, 2, generator=g, dtype=torch.float64), "placeholder": 0}
+            for i in range(40)]
+    a, b = tmp_path / "a.pkl", tmp_path / "b.pkl"
+    pickle.dump(recs[:25], open(a, "wb"))
+    pickle.dump(recs[25:], open(b, "wb"))
+    want = pickle.load(open(a, "rb")) + pickle.load(open(b, "rb"))
+    blob = pickle.dumps(torch.randn(4, generator=g))
+    calls = {"slow": 0}
+    slow = torch.storage._load_from_bytes
+
+    def counting(bts):
+        calls["slow"] += 1
+        return slow(bts)
+
+    monkeypatch.setattr(torch.storage, "_load_from_bytes", counting)
+    got = rp._read_records([str(a), str(b)])
+    assert calls["slow"] == 0                                  # everything took the direct parser
+    assert len(got) == len(want) == 40
+    for x, y in zip(got, want):
+        assert x.keys() == y.keys() and x["caption"] == y["caption"] and x["placeholder"] == 0
+        for key in ("text_embedding", "view", "row", "long", "half", "bf16", "bool", "empty", "scalar", "f64"):
+            assert type(x[key]) is torch.Tensor and x[key].dtype == y[key].dtype
+            assert x[key].shape == y[key].shape and x[key].stride() == y[key].stride()
+            assert torch.equal(x[key], y[key]) and not x[key].requires_grad
+    got[0]["text_embedding"][0, 0] = 7.0                       # owns writable memory
+    # unknown streams fall back to torch's loader
+    assert b"cpu" in blob
+    broken = blob.replace(b"cpu", b"xpu", 1)                   # a location the parser does not take
+    try:
+        rp._FastTensorUnpickler(__import__("io").BytesIO(broken)).load()
+    except Exception:
+        pass
+    assert calls["slow"] >= 1
+    monkeypatch.setenv("ZSAAC_FAST_UNPICKLE", "0")
+    calls["slow"] = 0
+    again = rp._read_records([str(a)])
+    assert calls["slow"] > 0 and torch.equal(again[3]["view"], want[3]["view"])
