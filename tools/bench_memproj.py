@@ -19,7 +19,8 @@ for (Q, N) in [(1, 49838), (1, 400_000), (4, 400_000), (1, 2_000_000), (8, 400_0
         e0.record(); map2memory(q, bank); e1.record(); torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     ms = statistics.median(times)
-    passes = -(-Q // 4)
+    # passes over the bank: one per query for banks >= 256 MB, one per pair of queries below
+    passes = Q if N * 1024 * 4 >= 256e6 else -(-Q // 2)
     gbs = passes * N * 1024 * 4 / (ms * 1e-3) / 1e9
     # torch reference formulation on the same GPU
     def ref():

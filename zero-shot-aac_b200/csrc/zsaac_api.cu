@@ -691,11 +691,15 @@ int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float*
     return fail(ZS_ERR_INVALID, "zs_memory_project: queries, bank and out must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // queries per pass over the bank: 2 (157 registers, 2 blocks per SM) streams at HBM speed;
-  // the 4-query instantiation needs 225 registers and was measured slower per query
-  constexpr int QB = 2;
+  // queries per pass over the bank.  Measured (profiles/r01/bench_map2memory.jsonl): against a
+  // 400 k-row bank one query per pass streams at 5.7 TB/s (0.29 ms), two per pass take 0.69 ms —
+  // the second accumulator set (157 registers) costs more than the second pass; the 4-query
+  // instantiation (225 registers) was slower still.  Small banks are launch-bound (three kernels
+  // per pass), so there two queries share a pass.
+  const int QB = (static_cast<double>(n_rows) * d * sizeof(float) >= 256e6) ? 1 : 2;
+  constexpr int QB_MAX = 2;
   const int blocks = ctx->sm_count * 2;
-  const int64_t need = static_cast<int64_t>(blocks) * QB * zs::memproj_partial_stride(d);
+  const int64_t need = static_cast<int64_t>(blocks) * QB_MAX * zs::memproj_partial_stride(d);
   if (need > ctx->memproj_elems) {
     if (ctx->memproj_partials) { ZS_CUDA(cudaFree(ctx->memproj_partials)); ctx->memproj_partials = nullptr; }
     ctx->memproj_elems = 0;
