@@ -215,7 +215,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import zsaac_b200
-    from zsaac_b200.sharded import ShardedRelatedBank, shard_bounds
+    from zsaac_b200.sharded import ShardedRelatedBank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
