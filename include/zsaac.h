@@ -160,6 +160,12 @@ int zs_gather_rows_f32(zs_ctx* ctx, const float* src, int64_t n_src_rows, int d,
  * query tile is split into, 256-row bank tiles per chunk, CTAs launched.  For tests / bench. */
 int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_chunk, int* n_ctas);
 
+/* The same planner for a hypothetical device and bank (no context, no GPU needed): sm_count SMs,
+ * bank_rows rows, cta_group 0 = choose per search, 1 / 2 = pinned.  lockstep_window receives the
+ * bank tiles per lock-step window (0 = lock-step off for this shape).  For host-side tests. */
+int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group, int* n_chunks,
+                int* tiles_per_chunk, int* n_ctas, int* lockstep_window);
+
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t zs_launch_count(const zs_ctx* ctx);
 

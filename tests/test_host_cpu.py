@@ -243,3 +243,49 @@ def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
     calls["slow"] = 0
     again = rp._read_records([str(a)])
     assert calls["slow"] > 0 and torch.equal(again[3]["view"], want[3]["view"])
+
+
+def _plan_dry(sm, n, q, k, cg=0):
+    lib = zsaac_b200.load_library()
+    a, b, c, w = (ctypes.c_int() for _ in range(4))
+    _abi.check(lib.zs_plan_dry(sm, n, q, k, cg, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                               ctypes.byref(w)))
+    return a.value, b.value, c.value, w.value
+
+
+def test_planner_invariants_and_baseline_plans(monkeypatch):
+    """The work-unit planner (bank chunks per query tile, tiles per chunk, CTAs, lock-step window)
+    runs without a GPU through zs_plan_dry: structural invariants on a grid of shapes, and the
+    plans of the BASELINE configs as measured on B200 (profiles/r01/bench_*.json)."""
+    import random
+    for var in ("ZSAAC_CHUNKS", "ZSAAC_LOCKSTEP", "ZSAAC_SYNC_WINDOW", "ZSAAC_CTA_GROUP"):
+        monkeypatch.delenv(var, raising=False)
+    rng = random.Random(5)
+    for _ in range(400):
+        sm = rng.choice([148, 132, 16, 2])
+        n = rng.choice([rng.randint(1, 3000), rng.randint(3000, 500_000), rng.randint(500_000, 20_000_000)])
+        q = rng.choice([rng.randint(1, 300), rng.randint(300, 70_000), rng.randint(70_000, 500_000)])
+        k = rng.randint(1, 32)
+        cg = rng.choice([0, 1, 2])
+        chunks, tpc, ctas, window = _plan_dry(sm, n, q, k, cg)
+        group = cg if cg else (2 if q > 256 else 1)
+        n_tiles = -(-n // 256)
+        m_tiles = -(-q // (128 * group))
+        assert 1 <= chunks <= min(n_tiles, 256)                 # two column halves each: <= 512 lists
+        assert chunks * tpc >= n_tiles > (chunks - 1) * tpc      # chunks cover the bank, none empty
+        assert ctas % group == 0 and group <= ctas <= max(sm // group, 1) * group
+        assert ctas // group == min(m_tiles * chunks, max(sm // group, 1))
+        assert window in (0, 32) and (window == 0 or (m_tiles > 1 and tpc >= 4 * window))
+    pins = {(10_000_000, 65_536, 32): (13, 3005, 148, 32),      # config 4, one GPU
+            (1_250_000, 65_536, 32): (2, 2442, 148, 32),        # config 4, one rank of eight
+            (400_000, 8_192, 10): (16, 98, 148, 0),             # config 3
+            (400_000, 400_000, 5): (5, 313, 148, 32),           # config 5
+            (49_838, 975, 10): (18, 11, 144, 0),                # config 2
+            (19_195, 1_045, 5): (13, 6, 130, 0),                # config 1
+            (400_000, 128, 10): (143, 11, 143, 0)}              # HBM-bound small batch
+    for (n, q, k), want in pins.items():
+        assert _plan_dry(148, n, q, k) == want, (n, q, k)
+    monkeypatch.setenv("ZSAAC_CHUNKS", "4")                      # tuning hook
+    assert _plan_dry(148, 400_000, 8_192, 10)[0] == 4
+    with pytest.raises(RuntimeError):
+        _plan_dry(148, 0, 10, 5)

@@ -496,6 +496,23 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
   return ZS_OK;
 }
 
+int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group, int* n_chunks,
+                int* tiles_per_chunk, int* n_ctas, int* lockstep_window) {
+  if (sm_count < 1 || bank_rows < 1 || Q < 1 || k < 1 || k > ZS_MAX_K || cta_group < 0 || cta_group > 2)
+    return fail(ZS_ERR_INVALID, "zs_plan_dry: sm_count=%d bank_rows=%lld Q=%lld k=%d cta_group=%d",
+                sm_count, (long long)bank_rows, (long long)Q, k, cta_group);
+  zs_ctx shape;                      // never touches a device: only the planner's inputs are set
+  shape.sm_count = sm_count;
+  shape.bank_rows = bank_rows;
+  shape.cta_group_override = cta_group;
+  const Plan pl = make_plan(&shape, Q, k);
+  if (n_chunks) *n_chunks = pl.chunks;
+  if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
+  if (n_ctas) *n_ctas = pl.ctas;
+  if (lockstep_window) *lockstep_window = pl.sync_window;
+  return ZS_OK;
+}
+
 int64_t zs_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int zs_kernel_error(const zs_ctx* ctx) { return (ctx && ctx->err_host) ? *ctx->err_host : 0; }
