@@ -231,6 +231,17 @@ def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
             assert x[key].shape == y[key].shape and x[key].stride() == y[key].stride()
             assert torch.equal(x[key], y[key]) and not x[key].requires_grad
     got[0]["text_embedding"][0, 0] = 7.0                       # owns writable memory
+    # plain pickling gives every tensor its own copy of the storage (torch's loader and this one)
+    for recs_ in (got, want):
+        assert (recs_[1]["view"].untyped_storage().data_ptr()
+                != recs_[1]["row"].untyped_storage().data_ptr())
+    assert got[1]["view"].untyped_storage().nbytes() == want[1]["view"].untyped_storage().nbytes()
+    # autograd state takes torch's own rebuild
+    leaf = torch.randn(3, generator=g).requires_grad_()
+    monkeypatch.undo()
+    back = rp._FastTensorUnpickler(__import__("io").BytesIO(pickle.dumps({"p": leaf}))).load()
+    assert back["p"].requires_grad and torch.equal(back["p"], leaf)
+    monkeypatch.setattr(torch.storage, "_load_from_bytes", counting)
     # unknown streams fall back to torch's loader
     assert b"cpu" in blob
     broken = blob.replace(b"cpu", b"xpu", 1)                   # a location the parser does not take

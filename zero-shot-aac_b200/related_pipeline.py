@@ -38,7 +38,8 @@ QUERY_BATCH = 16384
 # `int64 count | raw little-endian data` — and copies the raw bytes into a fresh storage.  Anything
 # unexpected (other magic / protocol, several storages, a non-CPU location, a length that does not
 # add up) goes to torch's own loader, so the records are identical either way; only the time
-# differs (load_data at 49,838 records: 2.6 -> 1.4 s).  ZSAAC_FAST_UNPICKLE=0 switches it off.
+# differs.  The tensor itself is then rebuilt as a strided view of that storage instead of through
+# torch._utils._rebuild_tensor_v2 (whose fake-mode detection costs another ~20 us per tensor).  ZSAAC_FAST_UNPICKLE=0 switches it off.
 _LEGACY_MAGIC = 0x1950a86a20f9469cfc6c
 _LEGACY_PROTOCOL = 1001
 _STORAGE_DTYPES = {
@@ -81,16 +82,42 @@ def _storage_from_legacy_bytes(b: bytes):
             flat = torch.empty(0, dtype=dtype)
         else:
             flat = torch.frombuffer(bytearray(memoryview(b)[pos + 8:]), dtype=dtype)
-        return torch.storage.TypedStorage(wrap_storage=flat.untyped_storage(), dtype=dtype,
-                                          _internal=True)
+        return _FlatStorage(flat)
     except Exception:
         return slow(b)
+
+
+class _FlatStorage:
+    """What _storage_from_legacy_bytes hands to the tensor rebuild: the storage's elements as a
+    flat tensor."""
+    __slots__ = ("flat",)
+
+    def __init__(self, flat: torch.Tensor):
+        self.flat = flat
+
+    def typed_storage(self):
+        return torch.storage.TypedStorage(wrap_storage=self.flat.untyped_storage(),
+                                          dtype=self.flat.dtype, _internal=True)
+
+
+def _rebuild_tensor_fast(storage, storage_offset, size, stride, requires_grad=False,
+                         backward_hooks=None, metadata=None):
+    """torch._utils._rebuild_tensor_v2 for the common case (plain tensor, no autograd state):
+    a strided view of the flat tensor, without torch's per-tensor fake-mode detection."""
+    if isinstance(storage, _FlatStorage):
+        if not requires_grad and not backward_hooks and not metadata:
+            return storage.flat.as_strided(tuple(size), tuple(stride), storage_offset)
+        storage = storage.typed_storage()
+    return torch._utils._rebuild_tensor_v2(storage, storage_offset, size, stride, requires_grad,
+                                           backward_hooks, metadata)
 
 
 class _FastTensorUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "torch.storage" and name == "_load_from_bytes":
             return _storage_from_legacy_bytes
+        if module == "torch._utils" and name == "_rebuild_tensor_v2":
+            return _rebuild_tensor_fast
         return super().find_class(module, name)
 
 
