@@ -14,6 +14,8 @@
  *   - work is enqueued on the cudaStream_t passed as `stream` (NULL = legacy default stream);
  *     no entry point synchronises the host except where stated (workspace growth)
  *   - there is no CPU fallback: on a machine without an sm_100 GPU zs_create fails
+ *   - a context is not thread-safe and owns one set of workspaces: use one context per host
+ *     thread / per concurrent stream (zs_last_error() is thread-local)
  *   - plain C types only; no torch / C++ types cross this boundary
  */
 #ifndef ZSAAC_H_
@@ -96,7 +98,12 @@ int zs_reserve(zs_ctx* ctx, int64_t Q, int k);
  *   index_offset     added to every returned index (first global row of this bank shard)
  *   out_scores       [Q, k] fp32, descending; ties broken by ascending index
  *   out_indices      [Q, k] int64 global indices
- * Requires 1 <= k <= min(ZS_MAX_K, bank rows [- 1 with self exclusion]). */
+ * Requires 1 <= k <= min(ZS_MAX_K, bank rows [- 1 with self exclusion]).
+ * Deterministic: the result is the exact top-k of the bf16 scores under (score desc, index asc)
+ * whatever the launch geometry or timing (the work units exchange admission thresholds while
+ * they run, which changes only how much each unit contributes, never the merged result).
+ * Three kernels are enqueued on `stream` (cast, fused similarity/top-k, merge); the context's
+ * workspaces are in use until they finish, so searches on one context must not overlap. */
 int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k,
               int normalize_queries, const int64_t* self_index, int64_t index_offset,
               float* out_scores, int64_t* out_indices, void* stream);
