@@ -46,7 +46,8 @@ typedef enum zs_dtype {
 } zs_dtype;
 
 /* Limits of the fused kernel. */
-#define ZS_MAX_K 32        /* top-k list length held in registers per query row              */
+#define ZS_PASS_K 32       /* top-k list length held in registers per query row and pass     */
+#define ZS_MAX_K 1024      /* k > ZS_PASS_K runs ceil(k / 32) passes over the bank           */
 #define ZS_DIM_MULTIPLE 64 /* embedding dim must be a multiple of the 128-byte bf16 K block  */
 #define ZS_MAX_DIM 4096
 
@@ -129,6 +130,31 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
  *   over the bank per group of 2 queries (the reference calls it with one audio embedding). */
 int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
                       int d, float temperature, float* out, void* stream);
+
+/* Exact fp32 top-k for SMALL banks (replaces `prefix @ bank.T -> softmax -> topk` of
+ * utils.py:133-135 — softmax is monotone — and the zero-shot classification step
+ * `audio_emb @ text_embeds.t() -> argmax`, retrieval/zero_shot_classification.py:97-103).
+ * Scores are fp32 FMA dot products (cosine with normalize != 0), i.e. the reference's own
+ * arithmetic class: indices equal the reference's except at fp32 rounding ties.  No bf16 bank:
+ *   queries [Q, d] fp32, bank [n_rows, d] fp32 (the caller's tensor, read in place), d % 4 == 0
+ *   self_index nullable [Q] global index to skip; index_offset = global index of bank row 0
+ *   out_scores [Q, k] fp32 descending, out_indices [Q, k] int64, ties by ascending index
+ * Up to 64 queries are ONE launch (the last block to finish selects); Q * n_rows <= 2^30. */
+int zs_exact_topk_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, int normalize, int k, const int64_t* self_index, int64_t index_offset,
+                      float* out_scores, int64_t* out_indices, void* stream);
+
+/* Exact fp32 rank of ground-truth items (the retrieval metrics a2t / t2a at their real sizes,
+ * reference retrieval/tools/utils.py:182-192,232-237: cos_sim -> argsort -> np.where).
+ *   target_index [Q, n_targets] int64 global bank indices (< 0 = unused slot)
+ *   out_ranks    [Q, n_targets] int64: number of bank rows ranking BEFORE the target under
+ *                (score desc, index asc) — the target's position in zs_exact_topk_f32's order,
+ *                so tied ground truths get distinct positions; -1 for unused / absent targets
+ *   out_target_scores nullable [Q, n_targets] fp32 (+inf if unused)
+ * Same limits as zs_exact_topk_f32. */
+int zs_exact_rank_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, int normalize, const int64_t* target_index, int n_targets,
+                      int64_t index_offset, float* out_target_scores, int64_t* out_ranks, void* stream);
 
 /* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
  * bank chunks) under the total order (score desc, index asc).

@@ -49,7 +49,7 @@ class cuda_to_cpu:
         torch.Tensor.to = self._orig
 
 
-# ---- input recipes (shared with tests/fixtures.py: keep in sync) -----------------------------
+# ---- input recipes (shared with tests/helpers.py: keep in sync) -----------------------------
 def make_embeddings(case):
     rs = np.random.RandomState(case["seed"])
     n = case["n"]

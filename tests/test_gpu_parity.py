@@ -82,7 +82,7 @@ SHAPES = [
     (975, 49838, 10),     # BASELINE config 2: AudioCaps
     (1, 527, 3),          # one query vs an AudioSet-label-sized bank
     (3, 255, 1),          # single partial tile, k = 1
-    (130, 256, 32),       # k = ZS_MAX_K, exact tile multiple, 2 query tiles
+    (130, 256, 32),       # k = ZS_PASS_K, exact tile multiple, 2 query tiles
     (257, 70001, 17),     # ragged everywhere
     (64, 40, 32),         # k close to N
     (33, 33, 32),         # k = N - 1
@@ -236,7 +236,7 @@ def test_argument_errors_raise(zs):
     with pytest.raises(RuntimeError, match="out of range"):     # torch.topk wording
         rb.search(q, 41)
     with pytest.raises(RuntimeError, match="out of range"):
-        rb.search(q, 33)                                        # > ZS_MAX_K
+        rb.search(q, 1025)                                      # > ZS_MAX_K
     with pytest.raises(RuntimeError, match="out of range"):
         rb.search(q, 0)
     with pytest.raises(RuntimeError, match="out of range"):

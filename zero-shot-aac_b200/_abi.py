@@ -21,7 +21,8 @@ ZS_ERR_KERNEL = -5
 
 ZS_F32 = 0
 ZS_BF16 = 1
-ZS_MAX_K = 32
+ZS_PASS_K = 32      # list length per pass of the fused kernel
+ZS_MAX_K = 1024     # k > 32 runs ceil(k / 32) passes over the bank
 ZS_DIM_MULTIPLE = 64
 
 _c_ctx = ctypes.c_void_p
@@ -29,7 +30,7 @@ _i64 = ctypes.c_int64
 _int = ctypes.c_int
 _ptr = ctypes.c_void_p
 
-# name -> (restype, argtypes); mirrors include/zsaac.h one to one (tests/test_abi.py checks it)
+# name -> (restype, argtypes); mirrors include/zsaac.h one to one (tests/test_host_cpu.py checks it)
 SIGNATURES = {
     "zs_abi_version": (_int, []),
     "zs_last_error": (ctypes.c_char_p, []),
@@ -48,6 +49,10 @@ SIGNATURES = {
     "zs_merge": (_int, [_c_ctx, _ptr, _ptr, _int, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr]),
     "zs_rescore_f32": (_int, [_c_ctx, _ptr, _i64, _int, _ptr, _i64, _int, _i64, _ptr, _int, _int,
                               _ptr, _ptr, _ptr]),
+    "zs_exact_topk_f32": (_int, [_c_ctx, _ptr, _i64, _ptr, _i64, _int, _int, _int, _ptr, _i64, _ptr,
+                                 _ptr, _ptr]),
+    "zs_exact_rank_f32": (_int, [_c_ctx, _ptr, _i64, _ptr, _i64, _int, _int, _ptr, _int, _i64, _ptr,
+                                 _ptr, _ptr]),
     "zs_gather_rows_f32": (_int, [_c_ctx, _ptr, _i64, _int, _ptr, _i64, _ptr, _ptr]),
     "zs_plan": (_int, [_c_ctx, _i64, _int, ctypes.POINTER(_int), ctypes.POINTER(_int),
                        ctypes.POINTER(_int)]),

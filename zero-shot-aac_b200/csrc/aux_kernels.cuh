@@ -23,29 +23,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One warp per row.  d is a multiple of 4 (64 on the search path), so every lane handles whole
 // 8-byte/16-byte vectors.
 // The sum of squares is accumulated in a fixed order (lane-strided, then xor butterfly), so the
-// result does not depend on the launch geometry.
+// result does not depend on the launch geometry (nor on which kernel calls this).
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(256)
-normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
-                      int64_t n_rows_out, int d, int normalize, unsigned int* __restrict__ row_thr) {
-  // the consumer (fused search kernel) may begin its prologue now; it waits for this grid to
-  // finish before it reads `out`
-  ptx::pdl_launch_dependents();
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= n_rows_out) return;
-  // query side of a search: reset the row's shared admission threshold (SimTopkParams::row_thr)
-  if (row_thr != nullptr && lane == 0) row_thr[row] = 0u;
-  OutT* dst = out + row * d;
-  if (row >= n_rows) {
-    // padding rows [n_rows, n_rows_out): zeros, so the consumer's TMA boxes never leave the tensor
-    for (int c = lane * 4; c < d; c += 128) {
-      if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      else *reinterpret_cast<uint2*>(dst + c) = make_uint2(0u, 0u);
-    }
-    return;
-  }
-  const InT* src = in + row * d;
+__device__ __forceinline__ void normalize_cast_row(const InT* __restrict__ src, OutT* __restrict__ dst,
+                                                   int d, int normalize, int lane) {
   float denom = 1.0f;   // F.normalize divides by max(||x||, eps); x / 1 is exact when not normalising
   if (normalize) {
     float ss = 0.0f;
@@ -87,6 +68,29 @@ normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_
       *reinterpret_cast<uint2*>(dst + c) = packed;
     }
   }
+}
+
+// Zero row (query workspace padding: the consumer's TMA boxes never leave the tensor).
+template <typename OutT>
+__device__ __forceinline__ void zero_row(OutT* __restrict__ dst, int d, int lane) {
+  for (int c = lane * 4; c < d; c += 128) {
+    if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    else *reinterpret_cast<uint2*>(dst + c) = make_uint2(0u, 0u);
+  }
+}
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const InT* __restrict__ in, OutT* __restrict__ out, int64_t n_rows,
+                      int64_t n_rows_out, int d, int normalize) {
+  // the consumer (fused search kernel) may begin its prologue now; it waits for this grid to
+  // finish before it reads `out`
+  ptx::pdl_launch_dependents();
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows_out) return;
+  if (row >= n_rows) { zero_row(out + row * d, d, lane); return; }   // rows [n_rows, n_rows_out)
+  normalize_cast_row(in + row * d, out + row * d, d, normalize, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,7 +179,7 @@ template <typename IdxT, int LPL>
 __global__ void __launch_bounds__(256)
 merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
                    int64_t score_stride, int64_t index_stride, int64_t Q, int k, long long idx_offset,
-                   float* __restrict__ out_scores, long long* __restrict__ out_idx) {
+                   float* __restrict__ out_scores, long long* __restrict__ out_idx, int64_t out_stride) {
   ptx::pdl_wait();   // lists are written by the preceding grid (no-op without the PDL attribute)
   const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,8 +192,8 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
         i = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k + pos]);
       },
       [&](int r, float s, long long i) {
-        out_scores[q * k + r] = s;
-        out_idx[q * k + r] = (i == SENT) ? -1ll : i + idx_offset;
+        out_scores[q * out_stride + r] = s;
+        out_idx[q * out_stride + r] = (i == SENT) ? -1ll : i + idx_offset;
       });
 }
 
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(32 * MERGE_BLOCK_WARPS)
 merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx, int S,
                          int64_t score_stride, int64_t index_stride, int64_t Q, int k,
                          long long idx_offset, float* __restrict__ out_scores,
-                         long long* __restrict__ out_idx) {
+                         long long* __restrict__ out_idx, int64_t out_stride) {
   __shared__ float part_s[MERGE_BLOCK_WARPS][MERGE_BLOCK_MAX_K];
   __shared__ long long part_i[MERGE_BLOCK_WARPS][MERGE_BLOCK_MAX_K];
   ptx::pdl_wait();
@@ -234,8 +238,8 @@ merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restric
           i = part_i[list][pos];
         },
         [&](int r, float s, long long i) {
-          out_scores[q * k + r] = s;
-          out_idx[q * k + r] = (i == SENT) ? -1ll : i + idx_offset;
+          out_scores[q * out_stride + r] = s;
+          out_idx[q * out_stride + r] = (i == SENT) ? -1ll : i + idx_offset;
         });
   }
 }
@@ -248,19 +252,21 @@ merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restric
 // from the caller's fp32 bank restores the fp32 ranking wherever the true top-k lies inside the
 // candidate set.
 //
-// One block (4 warps) per query: warps stride over the kc <= 32 candidates, each computes
-// q.b, q.q and b.b of one (query, candidate) pair in fp32 (16-byte loads, fixed summation order:
-// lane-strided, then xor butterfly) -> cosine = q.b / (max(|q|, eps) max(|b|, eps)), or the raw
-// q.b with normalize == 0; warp 0 then picks the k best under (score desc, index asc).
+// One block (4 warps) per query: warps stride over the kc candidates, each computes q.b, q.q and
+// b.b of one (query, candidate) pair in fp32 (16-byte loads, fixed summation order: lane-strided,
+// then xor butterfly) -> cosine = q.b / (max(|q|, eps) max(|b|, eps)), or the raw q.b with
+// normalize == 0; the block then sorts the candidates in shared memory (bitonic network over
+// P = next power of two >= kc entries) under (score desc, index asc) and writes the first k.
 constexpr int RESCORE_THREADS = 128;
-constexpr int RESCORE_MAX_CAND = 32;
+constexpr int RESCORE_MAX_CAND = 2048;
 __global__ void __launch_bounds__(RESCORE_THREADS)
 rescore_f32_kernel(const float* __restrict__ queries, const float* __restrict__ bank, int64_t n_bank,
                    int d, int normalize, const long long* __restrict__ cand, int kc, int k,
                    long long idx_offset, float* __restrict__ out_scores,
-                   long long* __restrict__ out_idx) {
-  __shared__ float s_score[RESCORE_MAX_CAND];
-  __shared__ long long s_idx[RESCORE_MAX_CAND];
+                   long long* __restrict__ out_idx, int P) {
+  extern __shared__ __align__(16) unsigned char rescore_smem[];
+  long long* s_idx = reinterpret_cast<long long*>(rescore_smem);   // [P]
+  float* s_score = reinterpret_cast<float*>(s_idx + P);            // [P]
   const int64_t q = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -288,26 +294,32 @@ rescore_f32_kernel(const float* __restrict__ queries, const float* __restrict__ 
     }
     if (lane == 0) { s_score[c] = score; s_idx[c] = keep; }
   }
+  for (int c = kc + static_cast<int>(threadIdx.x); c < P; c += RESCORE_THREADS) {
+    s_score[c] = -CUDART_INF_F;
+    s_idx[c] = SENT;
+  }
   __syncthreads();
-  if (warp == 0) {
-    Cand mine{-CUDART_INF_F, SENT, lane};
-    if (lane < kc) { mine.s = s_score[lane]; mine.i = s_idx[lane]; }
-    for (int r = 0; r < k; ++r) {
-      Cand best = mine;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        Cand other;
-        other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
-        other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-        other.src = __shfl_xor_sync(0xffffffffu, best.src, o);
-        if (cand_better(other, best)) best = other;
+  // bitonic sort, "better first" = (score desc, index asc)
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < P / 2; i += RESCORE_THREADS) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        const int hi = lo | stride;
+        const bool up = (lo & size) == 0;
+        const float sa = s_score[lo], sb = s_score[hi];
+        const long long ia = s_idx[lo], ib = s_idx[hi];
+        const bool b_better = (sb > sa) || (sb == sa && ib < ia);
+        if (b_better == up) {
+          s_score[lo] = sb; s_score[hi] = sa;
+          s_idx[lo] = ib; s_idx[hi] = ia;
+        }
       }
-      if (lane == 0) {
-        out_scores[q * k + r] = best.s;
-        out_idx[q * k + r] = (best.i == SENT) ? -1ll : best.i;
-      }
-      if (best.src == lane) { mine.s = -CUDART_INF_F; mine.i = SENT; mine.src = 64 + lane; }  // taken
+      __syncthreads();
     }
+  }
+  for (int r = threadIdx.x; r < k; r += RESCORE_THREADS) {
+    out_scores[q * k + r] = s_score[r];
+    out_idx[q * k + r] = (s_idx[r] == SENT) ? -1ll : s_idx[r];
   }
 }
 

@@ -26,6 +26,7 @@
 
 #include <math_constants.h>
 
+#include "aux_kernels.cuh"
 #include "ptx_sm100.cuh"
 
 namespace zs {
@@ -61,7 +62,8 @@ constexpr int smem_bytes() { return num_stages<CG>() * stage_bytes<CG>() + BARRI
 constexpr int IDX_SENTINEL = 0x7fffffff;
 
 // error codes written to the device flag by a timed-out wait
-enum : int { ERR_PRODUCER = 101, ERR_MMA_FULL = 102, ERR_MMA_TEMPTY = 103, ERR_EPILOGUE = 104 };
+enum : int { ERR_PRODUCER = 101, ERR_MMA_FULL = 102, ERR_MMA_TEMPTY = 103, ERR_EPILOGUE = 104,
+              ERR_GRID_CAST = 105, ERR_GRID_DONE = 106 };
 
 struct SimTopkParams {
   int Q;                 // query rows
@@ -105,7 +107,41 @@ struct SimTopkParams {
   // the global top-k, so units admit only v > pred(t) (the float just below t: elements EQUAL to
   // t may still win the index tie-break).  Lists then may hold fewer than k entries (the rest
   // stay -inf / IDX_SENTINEL); the merged result is the exact top-k whatever the timing.
-  unsigned int* row_thr;      // [Q padded], keys; zeroed per search by the query cast kernel
+  // Entries are 64-bit: (epoch << 32) | key.  Every search (every pass of a k > 32 search) uses a
+  // new epoch, so stale entries compare lower than any entry of the running search and are
+  // ignored by readers: the array never needs a reset.
+  unsigned long long* row_thr;   // [Q padded]
+  unsigned int epoch;
+  // Bootstrap of the admission threshold (nullable = off).  When all units of a query row start
+  // at the same time (small searches: one unit per CTA) nobody has a full list to publish yet.
+  // Every list therefore scans its FIRST bank tile twice: pass A only takes the maximum of its
+  // scores and publishes it to one of `boot_slots` (<= 32) slots of its row; the k-th largest of
+  // the row's slot maxima is a valid admission threshold at once (k distinct bank rows score at
+  // least that much), and about as tight as the k-th entry of a list that has seen
+  // boot_slots x more columns.  Pass B then scans the tile with that threshold.
+  unsigned long long* boot;      // [Q padded, BOOT_SLOTS] epoch-tagged keys
+  int boot_slots;                // min(number of lists per row, BOOT_SLOTS)
+  // k > 32: the search runs in passes of <= 32; pass p admits only elements strictly AFTER the
+  // last element of pass p-1 under (score desc, index asc).  bound_* point at that element for
+  // row 0 (inside the caller's output arrays), bound_stride = elements between rows.
+  const float* bound_scores;     // nullable
+  const long long* bound_idx;    // global indices
+  long long bound_stride;
+  // Single-launch ("solo") mode for small searches: the kernel is launched cooperatively, casts
+  // (and normalises) the queries itself in a distributed prologue and merges the partial lists
+  // itself after a grid-wide arrival counter, so a search is ONE launch instead of three.
+  int solo;
+  const void* q_src;             // raw queries [Q, d] (nullptr: the bf16 workspace is already filled)
+  int q_src_bf16;                // dtype of q_src
+  int q_normalize;
+  __nv_bfloat16* q_ws;           // bf16 query workspace [q_pad, d] the query tensor map points at
+  int q_pad;
+  int d;
+  unsigned long long* grid_cnt;  // [2] monotonic arrival counters: queries cast, lists written
+  unsigned long long cast_target, done_target;
+  float* out_scores;             // [Q, out_stride]
+  long long* out_idx;
+  long long out_stride;
 };
 
 // Order-preserving float -> uint32 key (unsigned compare == float compare, -0 < +0), so that
@@ -124,10 +160,25 @@ __device__ __forceinline__ float seed_below(unsigned int key) {
   // pred(+0) is -0, which still compares equal to +0: step once more, to the negative denormal
   return (f == 0.0f) ? __uint_as_float(0x80000001u) : f;
 }
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ float key_to_score(unsigned int key) {
+  return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// key of the running search, or 0 ("nothing published") for entries of older searches
+__device__ __forceinline__ unsigned int epoch_key(unsigned long long e, unsigned int epoch) {
+  return (static_cast<unsigned int>(e >> 32) == epoch) ? static_cast<unsigned int>(e) : 0u;
+}
+__device__ __forceinline__ unsigned long long make_epoch_key(unsigned int epoch, float f) {
+  return (static_cast<unsigned long long>(epoch) << 32) | score_key(f);
 }
 
 constexpr long long SYNC_WAIT_LIMIT_CYCLES = 600000;   // ~0.3-0.4 ms: then give up lock-step
@@ -192,6 +243,155 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
 #pragma unroll
   for (int t = 0; t < 2; ++t) d[t] = (j & 8) ? c[2 * t + 1] : c[2 * t];
   return (j & 16) ? d[1] : d[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bootstrap of the admission threshold (SimTopkParams::boot)
+constexpr int BOOT_SLOTS = 32;
+constexpr long long BOOT_WAIT_LIMIT_CYCLES = 6000;    // ~3 us: then take what has been published
+
+// Descending bitonic sort of 32 floats in registers (fully unrolled, every index a constant).
+__device__ __forceinline__ void sort32_desc(float (&a)[32]) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int l = i ^ stride;
+        if (l > i) {
+          const bool desc = (i & size) == 0;
+          const float lo = fminf(a[i], a[l]);
+          const float hi = fmaxf(a[i], a[l]);
+          a[i] = desc ? hi : lo;
+          a[l] = desc ? lo : hi;
+        }
+      }
+    }
+  }
+}
+
+// Pass A over the first bank tile of a unit (warp-collective: tcgen05.ld is .sync.aligned).
+//   taddr       tensor-memory address of this warp's lane quarter, first column of its half
+//   col_first   bank column of that first column
+// Publishes the maximum of the thread's EPI_COLS scores (ragged tail and the self column masked)
+// to slot `slot` of its row, waits a bounded time for `expect` slots of the row, and returns the
+// admission seed: the largest float strictly below the k-th largest slot maximum (-inf while
+// fewer than k slots are filled).  Valid because the slot maxima are scores of distinct bank rows.
+__device__ __noinline__ float boot_threshold(uint32_t taddr, int col_first, int n_bank, int self_col,
+                                             bool row_ok, unsigned long long* slots_row, int slot,
+                                             int expect, int k, unsigned int epoch) {
+  float m = -CUDART_INF_F;
+#pragma unroll 1
+  for (int c = 0; c < EPI_COLS; c += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(taddr + c, r);
+    ptx::tmem_ld_wait();
+    const int col0 = col_first + c;
+    const bool clean = (col0 + 32 <= n_bank) && !(self_col >= col0 && self_col < col0 + 32);
+    if (clean) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < n_bank && col0 + j != self_col) m = fmaxf(m, __uint_as_float(r[j]));
+    }
+  }
+  if (row_ok) atomicMax(slots_row + slot, make_epoch_key(epoch, m));
+  float v[32];
+  const long long w0 = clock64();
+  while (true) {
+    int filled = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      unsigned long long e0, e1;
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+                   : "=l"(e0), "=l"(e1) : "l"(slots_row + j) : "memory");
+      const unsigned int k0 = epoch_key(e0, epoch), k1 = epoch_key(e1, epoch);
+      filled += (k0 != 0u) + (k1 != 0u);
+      v[j] = k0 ? key_to_score(k0) : -CUDART_INF_F;
+      v[j + 1] = k1 ? key_to_score(k1) : -CUDART_INF_F;
+    }
+    const bool ok = (filled >= expect) || !row_ok || (clock64() - w0 > BOOT_WAIT_LIMIT_CYCLES);
+    if (__all_sync(0xffffffffu, ok)) break;
+    __nanosleep(64);
+  }
+  sort32_desc(v);
+  uint32_t vb[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) vb[j] = __float_as_uint(v[j]);
+  const float kth = __uint_as_float(select32(vb, k - 1));
+  return seed_below(score_key(kth));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solo mode helpers
+// All lanes poll (one coalesced request per try); straight-line asm so that the callers keep
+// warp-uniform control flow.  Cooperative launch guarantees that every CTA of the grid is
+// resident, so the wait always ends; the bound only turns a bug into a trap.
+__device__ __forceinline__ void grid_wait(const unsigned long long* cnt, unsigned long long target,
+                                          int* err, int code) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, has_err;\n\t"
+      ".reg .u64 v;\n\t"
+      ".reg .u32 tries;\n\t"
+      "mov.u32 tries, 0;\n\t"
+      "ZS_GRID_WAIT_LOOP:\n\t"
+      "ld.acquire.gpu.global.u64 v, [%0];\n\t"
+      "setp.ge.u64 p, v, %1;\n\t"
+      "@p bra ZS_GRID_WAIT_DONE;\n\t"
+      "nanosleep.u32 32;\n\t"
+      "add.u32 tries, tries, 1;\n\t"
+      "setp.lt.u32 q, tries, 0x4000000;\n\t"
+      "@q bra ZS_GRID_WAIT_LOOP;\n\t"
+      "setp.ne.u64 has_err, %2, 0;\n\t"
+      "@has_err st.volatile.global.u32 [%2], %3;\n\t"
+      "fence.sc.sys;\n\t"
+      "trap;\n\t"
+      "ZS_GRID_WAIT_DONE:\n\t"
+      "}" ::"l"(cnt), "l"(target), "l"(reinterpret_cast<uint64_t>(err)), "r"(code)
+      : "memory");
+}
+
+template <int LPL>
+__device__ __forceinline__ void solo_merge_row(const float* part_scores, const int* part_idx,
+                                               int n_lists, size_t list_stride, int row, int k,
+                                               long long index_offset, float* out_scores,
+                                               long long* out_idx, long long out_stride, int lane) {
+  const long long SENT = 0x7fffffffffffffffll;
+  // the lists were written by other CTAs of this same launch: read them through L2 (.cg), never
+  // through the non-coherent path
+  warp_merge<LPL>(
+      n_lists, k, lane,
+      [&](int list, int pos, float& sc, long long& ix) {
+        const size_t o = static_cast<size_t>(list) * list_stride + static_cast<size_t>(row) * k + pos;
+        sc = __ldcg(part_scores + o);
+        ix = widen_index(__ldcg(part_idx + o));
+      },
+      [&](int r, float sc, long long ix) {
+        out_scores[static_cast<size_t>(row) * out_stride + r] = sc;
+        out_idx[static_cast<size_t>(row) * out_stride + r] = (ix == SENT) ? -1ll : ix + index_offset;
+      });
+}
+
+// Rows are dealt round-robin to all warps of the grid.
+__device__ __noinline__ void solo_merge(const float* part_scores, const int* part_idx, int n_lists,
+                                        int Q, int k, long long index_offset, float* out_scores,
+                                        long long* out_idx, long long out_stride, int gwarp,
+                                        int n_gwarps, int lane) {
+  const size_t list_stride = static_cast<size_t>(Q) * k;
+  for (int row = gwarp; row < Q; row += n_gwarps) {
+    if (n_lists <= 32)
+      solo_merge_row<1>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
+    else if (n_lists <= 64)
+      solo_merge_row<2>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
+    else if (n_lists <= 256)
+      solo_merge_row<8>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
+    else
+      solo_merge_row<16>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
+  }
 }
 
 // MODE_TOPK: running top-k (KCAP list slots).  MODE_DUMP: write the score matrix (test hook).
@@ -262,6 +462,31 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int num_workers = static_cast<int>(gridDim.x) / CG;
   const int num_units = p.num_m_tiles * p.num_chunks;
 
+  // Solo mode, distributed prologue: the warps of the whole grid share the rows of the query
+  // batch (F.normalize + bf16 cast into the workspace the query tensor map points at); the TMA
+  // producers wait for the grid-wide arrival counter before their first query load.
+  if (MODE == MODE_TOPK && p.solo != 0 && p.q_src != nullptr) {
+    const int n_gwarps = static_cast<int>(gridDim.x) * (NUM_THREADS / 32);
+    for (int r = static_cast<int>(blockIdx.x) * (NUM_THREADS / 32) + warp; r < p.q_pad; r += n_gwarps) {
+      __nv_bfloat16* dst = p.q_ws + static_cast<size_t>(r) * p.d;
+      if (r >= p.Q) {
+        zero_row(dst, p.d, lane);
+      } else if (p.q_src_bf16) {
+        normalize_cast_row(static_cast<const __nv_bfloat16*>(p.q_src) + static_cast<size_t>(r) * p.d,
+                           dst, p.d, p.q_normalize, lane);
+      } else {
+        normalize_cast_row(static_cast<const float*>(p.q_src) + static_cast<size_t>(r) * p.d, dst,
+                           p.d, p.q_normalize, lane);
+      }
+    }
+    // generic-proxy writes, read by other CTAs' TMA (async proxy): proxy fence + gpu-scope fence
+    // on the writer side, counter acquire + proxy fence on the reader side
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.grid_cnt, 1ull);
+  }
+
   // The producer and the MMA issuer run their loops with the WHOLE warp (all values warp-uniform)
   // and elect one lane only around the instructions that must be issued once.  Inside an
   // `if (lane == 0)` region the compiler cannot use the uniform datapath, and every
@@ -281,6 +506,10 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const bool sync_on = (p.sync_cnt != nullptr) && is_leader;   // the leader paces the pair
     bool sync_wait = sync_on;
     int iter = 0;
+    if (MODE == MODE_TOPK && p.solo != 0 && p.q_src != nullptr) {
+      grid_wait(p.grid_cnt, p.cast_target, p.err_flag, ERR_GRID_CAST);   // every CTA has cast its rows
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
     for (int u = worker; u < num_units; u += num_workers, ++iter) {
       const int m_tile = u % p.num_m_tiles;
       const int chunk = u / p.num_m_tiles;
@@ -410,9 +639,24 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const bool share = (MODE == MODE_TOPK) && p.row_thr != nullptr && row < p.Q;
       float seed = -CUDART_INF_F;
       float published = -CUDART_INF_F;
-      unsigned int seed_key = 0;
-      if (share) seed_key = ld_relaxed_u32(p.row_thr + row);
+      unsigned long long seed_entry = 0;
+      if (share) seed_entry = ld_relaxed_u64(p.row_thr + row);
       float thr = list.threshold();
+      // k > 32, pass >= 2: only elements strictly after (bound_s, bound_col) in the result order
+      const bool bounded = (MODE == MODE_TOPK) && p.bound_scores != nullptr;
+      float bound_s = CUDART_INF_F;
+      long long bound_col = -1;
+      if (bounded && row < p.Q) {
+        bound_s = p.bound_scores[static_cast<size_t>(row) * p.bound_stride];
+        bound_col = p.bound_idx[static_cast<size_t>(row) * p.bound_stride] - p.index_offset;
+      }
+      // bootstrap (first wave only: later units inherit thresholds through row_thr)
+      int boot_expect = 0;
+      if (MODE == MODE_TOPK && p.boot != nullptr && u == worker && m_tile < num_workers) {
+        const int chunks_now = min((num_workers - 1 - m_tile) / p.num_m_tiles + 1, p.num_chunks);
+        boot_expect = min(p.boot_slots, chunks_now * EPI_HALVES);
+        if (boot_expect < p.k) boot_expect = 0;    // fewer concurrent lists than k: nothing to gain
+      }
       // RANK mode state (KCAP = target slots)
       float ts[KCAP];
       int tc[KCAP];
@@ -439,9 +683,18 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if constexpr (MODE == MODE_TOPK) {
           // the key was requested one tile ago (at unit start for the first tile), so its latency
           // is hidden behind a whole tile of scanning; the next one is requested right away
-          seed = fmaxf(seed, seed_below(seed_key));
+          seed = fmaxf(seed, seed_below(epoch_key(seed_entry, p.epoch)));
+          if (boot_expect > 0 && t == t0) {
+            __syncwarp();
+            const int list_id = chunk * EPI_HALVES + half;
+            const int row_c = min(row, p.q_pad - 1);
+            seed = fmaxf(seed, boot_threshold(tmem_base + tmem_lane + acc * BLOCK_N + half * EPI_COLS,
+                                              col_tile + half * EPI_COLS, p.n_bank, self_col, row < p.Q,
+                                              p.boot + static_cast<size_t>(row_c) * BOOT_SLOTS,
+                                              list_id % p.boot_slots, boot_expect, p.k, p.epoch));
+          }
           thr = fmaxf(thr, seed);
-          if (share) seed_key = ld_relaxed_u32(p.row_thr + row);
+          if (share) seed_entry = ld_relaxed_u64(p.row_thr + row);
         }
 #pragma unroll 1
         for (int c0 = half * EPI_COLS; c0 < (half + 1) * EPI_COLS; c0 += 32) {
@@ -495,7 +748,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 cand &= cand - 1;
                 const float v = __uint_as_float(select32(r, j));
                 const int col = col0 + j;
-                if (v > thr && col < p.n_bank && col != self_col) {
+                if (v > thr && col < p.n_bank && col != self_col &&
+                    (!bounded || v < bound_s || (v == bound_s && static_cast<long long>(col) > bound_col))) {
                   list.insert(v, col);
                   thr = fmaxf(list.threshold(), seed);
                 }
@@ -515,7 +769,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (share) {
             const float kth = list.threshold();      // > -inf only once the list holds k entries
             if (kth > published) {
-              atomicMax(p.row_thr + row, score_key(kth));   // result unused: a fire-and-forget RED
+              atomicMax(p.row_thr + row, make_epoch_key(p.epoch, kth));   // result unused: a fire-and-forget RED
               published = kth;
             }
           }
@@ -542,6 +796,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
           }
         }
+        if (p.solo != 0) __threadfence();   // the lists are merged by other CTAs of this launch
       }
     }
   }
@@ -551,6 +806,21 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+  if constexpr (MODE == MODE_TOPK) {
+    if (p.solo != 0) {
+      // Solo mode, distributed merge: once every CTA has written (and fenced) its partial lists,
+      // the warps of the whole grid share the query rows and merge the lists of each.
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(p.grid_cnt + 1, 1ull);
+      }
+      grid_wait(p.grid_cnt + 1, p.done_target, p.err_flag, ERR_GRID_DONE);
+      solo_merge(p.part_scores, p.part_idx, p.num_chunks * EPI_HALVES, p.Q, p.k, p.index_offset,
+                 p.out_scores, p.out_idx, p.out_stride,
+                 static_cast<int>(blockIdx.x) * (NUM_THREADS / 32) + warp,
+                 static_cast<int>(gridDim.x) * (NUM_THREADS / 32), lane);
+    }
+  }
   if (threadIdx.x == 0) {
     trace_stamp(p, 5);                                       // exit
     if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + 7] = clock64();

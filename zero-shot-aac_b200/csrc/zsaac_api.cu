@@ -18,6 +18,7 @@
 
 #include "../../include/zsaac.h"
 #include "aux_kernels.cuh"
+#include "exact_f32_kernels.cuh"
 #include "memproj_kernel.cuh"
 #include "simtopk_kernel.cuh"
 
@@ -79,7 +80,14 @@ struct zs_ctx {
 
   __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
   int64_t q_ws_rows = 0;
-  unsigned int* row_thr = nullptr;  // [q_ws_rows] shared admission thresholds (SimTopkParams::row_thr)
+  unsigned long long* row_thr = nullptr;  // [q_ws_rows] shared admission thresholds (SimTopkParams::row_thr)
+  unsigned long long* boot = nullptr;     // [q_ws_rows, BOOT_SLOTS] bootstrap slot maxima (SimTopkParams::boot)
+  unsigned int epoch = 0;                 // tags row_thr / boot entries; bumped per search pass
+  unsigned long long* grid_cnt = nullptr; // [2] monotonic arrival counters of the single-launch mode
+  unsigned long long cnt_base[2] = {0, 0};
+  int solo_state = 0;                     // 0 = not probed, 1 = cooperative launch works, -1 = unavailable
+  int solo_override = -1;                 // env ZSAAC_SOLO=0|1 (tests / A-B runs); -1 = choose per search
+  bool boot_enabled = true;               // env ZSAAC_BOOT=0 switches the threshold bootstrap off
   float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
   int64_t part_elems = 0;
@@ -93,6 +101,9 @@ struct zs_ctx {
   int64_t memproj_elems = 0;
   unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
   int64_t sync_cnt_elems = 0;
+  float* exact_scores = nullptr;      // zs_exact_*: [Q, n_rows] fp32 score scratch
+  int64_t exact_elems = 0;
+  unsigned int* exact_counter = nullptr;   // "last block done" ticket of the fused exact top-k
 
   int64_t launches = 0;
 
@@ -138,12 +149,13 @@ struct Plan {
 
 constexpr int kSyncWindowTiles = 32;   // 32 tiles x 512 KiB = 16 MiB of bank per window
 
-// CTA pairs (cta_group::2, 256-row query tiles, half the shared-memory traffic per MMA) pay off
-// once there are several query tiles; a single 128-row tile streams the bank fastest from
-// independent CTAs.
+// CTA pairs (cta_group::2, 256-row query tiles, half the shared-memory fill per MMA) as soon as
+// the batch exceeds one 128-row tile: a single CTA would have to refill 768 KiB of operands per
+// bank tile (6.4 us at the ~120 GB/s one SM can pull from L2, against 4.3 us of MMA), a CTA of a
+// pair only 512 KiB.  A single 128-row tile streams the bank fastest from independent CTAs.
 int pick_cta_group(const zs_ctx* ctx, int64_t Q) {
   if (ctx->cta_group_override) return ctx->cta_group_override;
-  return Q > 256 ? 2 : 1;
+  return Q > zs::BLOCK_M ? 2 : 1;
 }
 
 // Split the bank into `chunks` contiguous runs of 256-row tiles so that (query tiles x chunks)
@@ -207,8 +219,13 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
   if (q_pad > ctx->q_ws_rows) {
     if (ctx->q_ws) { ZS_CUDA(cudaFree(ctx->q_ws)); ctx->q_ws = nullptr; ctx->q_ws_rows = 0; }
     if (ctx->row_thr) { ZS_CUDA(cudaFree(ctx->row_thr)); ctx->row_thr = nullptr; }
+    if (ctx->boot) { ZS_CUDA(cudaFree(ctx->boot)); ctx->boot = nullptr; }
     ZS_CUDA(cudaMalloc(&ctx->q_ws, static_cast<size_t>(q_pad) * ctx->bank_d * sizeof(__nv_bfloat16)));
-    ZS_CUDA(cudaMalloc(&ctx->row_thr, static_cast<size_t>(q_pad) * sizeof(unsigned int)));
+    ZS_CUDA(cudaMalloc(&ctx->row_thr, static_cast<size_t>(q_pad) * sizeof(unsigned long long)));
+    ZS_CUDA(cudaMalloc(&ctx->boot, static_cast<size_t>(q_pad) * zs::BOOT_SLOTS * sizeof(unsigned long long)));
+    // entries are epoch-tagged: zero once, never reset again
+    ZS_CUDA(cudaMemset(ctx->row_thr, 0, static_cast<size_t>(q_pad) * sizeof(unsigned long long)));
+    ZS_CUDA(cudaMemset(ctx->boot, 0, static_cast<size_t>(q_pad) * zs::BOOT_SLOTS * sizeof(unsigned long long)));
     ctx->q_ws_rows = q_pad;
   }
   const Plan pl = make_plan(ctx, Q, k);
@@ -232,10 +249,10 @@ int ensure_workspace(zs_ctx* ctx, int64_t Q, int k) {
 
 template <typename InT>
 void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int64_t rows_out, int d,
-                      int normalize, unsigned int* row_thr, cudaStream_t st) {
+                      int normalize, cudaStream_t st) {
   const int64_t blocks = (rows_out * 32 + 255) / 256;
   zs::normalize_cast_kernel<InT, __nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      static_cast<const InT*>(in), out, rows, rows_out, d, normalize, row_thr);
+      static_cast<const InT*>(in), out, rows, rows_out, d, normalize);
 }
 
 
@@ -245,7 +262,8 @@ void launch_normalize(const void* in, __nv_bfloat16* out, int64_t rows, int64_t 
 template <typename IdxT>
 cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t score_stride,
                          int64_t index_stride, int64_t Q, int k, long long idx_offset,
-                         float* out_scores, long long* out_idx, bool pdl, cudaStream_t st) {
+                         float* out_scores, long long* out_idx, int64_t out_stride, bool pdl,
+                         cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>((Q * 32 + 255) / 256));
   cfg.blockDim = dim3(256);
@@ -262,16 +280,16 @@ cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t sc
     cfg.gridDim = dim3(static_cast<unsigned>(Q));
     cfg.blockDim = dim3(32 * zs::MERGE_BLOCK_WARPS);
     return cudaLaunchKernelEx(&cfg, zs::merge_lists_block_kernel<IdxT>, scores, idx, S, score_stride,
-                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+                              index_stride, Q, k, idx_offset, out_scores, out_idx, out_stride);
   }
   if (S <= 64)
     return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 2>, scores, idx, S, score_stride,
-                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+                              index_stride, Q, k, idx_offset, out_scores, out_idx, out_stride);
   if (S <= 256)
     return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 8>, scores, idx, S, score_stride,
-                              index_stride, Q, k, idx_offset, out_scores, out_idx);
+                              index_stride, Q, k, idx_offset, out_scores, out_idx, out_stride);
   return cudaLaunchKernelEx(&cfg, zs::merge_lists_kernel<IdxT, 16>, scores, idx, S, score_stride,
-                            index_stride, Q, k, idx_offset, out_scores, out_idx);
+                            index_stride, Q, k, idx_offset, out_scores, out_idx, out_stride);
 }
 
 template <int KCAP, int CG, int MODE>
@@ -289,8 +307,13 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   cfg.blockDim = dim3(zs::NUM_THREADS);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n_attr = 0;
+  if (p.solo != 0) {     // grid-wide arrival counters inside the kernel: every CTA must be resident
+    attr[n_attr].id = cudaLaunchAttributeCooperative;
+    attr[n_attr].val.cooperative = 1;
+    ++n_attr;
+  }
   if (CG == 2) {
     attr[n_attr].id = cudaLaunchAttributeClusterDimension;
     attr[n_attr].val.clusterDim.x = 2;
@@ -298,7 +321,7 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
     attr[n_attr].val.clusterDim.z = 1;
     ++n_attr;
   }
-  if (ctx->pdl_next) {   // the query normalise/cast kernel was enqueued just before this launch
+  if (ctx->pdl_next && p.solo == 0) {   // the query normalise/cast kernel was enqueued just before this launch
     attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
     ++n_attr;
@@ -308,7 +331,15 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   const bool prof = ctx->profiling && MODE != zs::MODE_DUMP;
   const int slot = ctx->prof_count % ZS_PROFILE_RING;
   if (prof) ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot], st));
-  ZS_CUDA(cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p));
+  {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p);
+    if (le != cudaSuccess && p.solo != 0) {
+      cudaGetLastError();          // not sticky: the caller falls back to the three-launch path
+      return fail(ZS_ERR_STATE, "cooperative launch unavailable: %s", cudaGetErrorString(le));
+    }
+    if (le != cudaSuccess)
+      return fail(ZS_ERR_CUDA, "cudaLaunchKernelEx(zs_simtopk_kernel) failed: %s", cudaGetErrorString(le));
+  }
   if (prof) {
     ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot + 1], st));
     ctx->prof_count += 1;
@@ -338,9 +369,9 @@ int prepare_queries(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, in
                     CUtensorMap* qmap, cudaStream_t st) {
   const int64_t q_pad = padded_query_rows(Q);
   if (q_dtype == ZS_F32)
-    launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, ctx->row_thr, st);
+    launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
   else
-    launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, ctx->row_thr, st);
+    launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return encode_rows_map(ctx, qmap, ctx->q_ws, q_pad, ctx->bank_d, zs::BLOCK_M);
@@ -388,6 +419,13 @@ int zs_create(zs_ctx** out, int device) {
   if (cg && (cg[0] == '1' || cg[0] == '2')) ctx->cta_group_override = cg[0] - '0';
   const char* pdl = getenv("ZSAAC_PDL");
   if (pdl && pdl[0] == '0') ctx->pdl_enabled = false;
+  const char* solo = getenv("ZSAAC_SOLO");
+  if (solo && (solo[0] == '0' || solo[0] == '1')) ctx->solo_override = solo[0] - '0';
+  const char* boot = getenv("ZSAAC_BOOT");
+  if (boot && boot[0] == '0') ctx->boot_enabled = false;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop)
+    ctx->solo_state = -1;
   // the role code of a timed-out pipeline wait goes to mapped host memory, so that it can still
   // be read after the trap has poisoned the CUDA context
   e = cudaHostAlloc(&ctx->err_host, sizeof(int), cudaHostAllocMapped);
@@ -400,6 +438,14 @@ int zs_create(zs_ctx** out, int device) {
     delete ctx;
     return fail(ZS_ERR_CUDA, "zs_create: mapped host allocation failed: %s", cudaGetErrorString(e));
   }
+  e = cudaMalloc(&ctx->grid_cnt, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(ctx->grid_cnt, 0, 2 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    cudaFreeHost(ctx->err_host);
+    if (ctx->grid_cnt) cudaFree(ctx->grid_cnt);
+    delete ctx;
+    return fail(ZS_ERR_CUDA, "zs_create: counter allocation failed: %s", cudaGetErrorString(e));
+  }
   *out = ctx;
   return ZS_OK;
 }
@@ -410,10 +456,14 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->bank);
   cudaFree(ctx->q_ws);
   cudaFree(ctx->row_thr);
+  cudaFree(ctx->boot);
+  cudaFree(ctx->grid_cnt);
   cudaFree(ctx->part_scores);
   cudaFree(ctx->part_idx);
   cudaFreeHost(ctx->err_host);
   cudaFree(ctx->sync_cnt);
+  cudaFree(ctx->exact_scores);
+  cudaFree(ctx->exact_counter);
   cudaFree(ctx->memproj_partials);
   cudaFree(ctx->tgt_scores);
   cudaFree(ctx->tgt_cols);
@@ -469,8 +519,8 @@ int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* dst = ctx->bank + dst_row * ctx->bank_d;
-  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, nullptr, st);
-  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, nullptr, st);
+  if (in_dtype == ZS_F32) launch_normalize<float>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
+  else launch_normalize<__nv_bfloat16>(rows, dst, n_rows, n_rows, ctx->bank_d, normalize, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -483,13 +533,13 @@ int zs_reserve(zs_ctx* ctx, int64_t Q, int k) {
   if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_reserve: no bank");
   if (Q < 1 || k < 1 || k > ZS_MAX_K) return fail(ZS_ERR_INVALID, "zs_reserve: Q=%lld k=%d", (long long)Q, k);
   DeviceGuard guard(ctx->device);
-  return ensure_workspace(ctx, Q, k);
+  return ensure_workspace(ctx, Q, std::min(k, (int)ZS_PASS_K));
 }
 
 int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_chunk, int* n_ctas) {
   if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_plan: no bank");
-  if (Q < 1) return fail(ZS_ERR_INVALID, "zs_plan: Q=%lld", (long long)Q);
-  const Plan pl = make_plan(ctx, Q, k);
+  if (Q < 1 || k < 1) return fail(ZS_ERR_INVALID, "zs_plan: Q=%lld k=%d", (long long)Q, k);
+  const Plan pl = make_plan(ctx, Q, std::min(k, (int)ZS_PASS_K));
   if (n_chunks) *n_chunks = pl.chunks;
   if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
   if (n_ctas) *n_ctas = pl.ctas;
@@ -505,7 +555,7 @@ int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group
   shape.sm_count = sm_count;
   shape.bank_rows = bank_rows;
   shape.cta_group_override = cta_group;
-  const Plan pl = make_plan(&shape, Q, k);
+  const Plan pl = make_plan(&shape, Q, std::min(k, (int)ZS_PASS_K));
   if (n_chunks) *n_chunks = pl.chunks;
   if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
   if (n_ctas) *n_ctas = pl.ctas;
@@ -548,10 +598,150 @@ int zs_profile_read(zs_ctx* ctx, float* ms_out, int max_entries, int* n_entries)
   return ZS_OK;
 }
 
+// A pipeline wait that timed out traps and poisons the CUDA context; the role code survives in
+// mapped host memory.  Every search-type entry point reports it instead of enqueueing more work.
+#define ZS_CHECK_KERNEL_FLAG(ctx, fn)                                                            \
+  do {                                                                                           \
+    if ((ctx)->err_host && *(ctx)->err_host != 0)                                                \
+      return fail(ZS_ERR_KERNEL, fn ": an earlier kernel timed out in pipeline role %d and "     \
+                  "trapped; the CUDA context of this process is unusable", *(ctx)->err_host);    \
+  } while (0)
+
+namespace {
+
+// Small searches run as ONE cooperative launch (in-kernel query cast + in-kernel merge).
+constexpr int64_t kSoloMaxQueries = 4096;
+
+bool solo_wanted(zs_ctx* ctx, int64_t Q, const Plan& pl) {
+  if (ctx->solo_state < 0 || ctx->solo_override == 0) return false;
+  if (ctx->profiling && ctx->solo_override != 1) {
+    // (profiling brackets the fused kernel alone; solo is still profiled as a whole when forced)
+  }
+  if (pl.ctas > ctx->sm_count) return false;
+  if (ctx->solo_override == 1) return true;
+  return Q <= kSoloMaxQueries;
+}
+
+// One pass of a search: the k_pass best elements that come strictly after the element
+// (bound_scores[q], bound_idx[q]) of every query (no bound on the first pass), written to
+// out_scores / out_indices with `out_stride` elements between rows.
+int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_pass, int normalize,
+                bool cast_queries, const int64_t* self_index, int64_t index_offset,
+                const float* bound_scores, const int64_t* bound_idx, float* out_scores,
+                int64_t* out_indices, int64_t out_stride, const Plan& pl, cudaStream_t st) {
+  const int64_t q_pad = padded_query_rows(Q);
+  bool solo = solo_wanted(ctx, Q, pl);
+  ctx->epoch += 1;
+  if (ctx->epoch == 0) {   // 2^32 passes later: stale entries could alias a live epoch, so wipe them once
+    ZS_CUDA(cudaMemsetAsync(ctx->row_thr, 0, static_cast<size_t>(ctx->q_ws_rows) * sizeof(unsigned long long), st));
+    ZS_CUDA(cudaMemsetAsync(ctx->boot, 0, static_cast<size_t>(ctx->q_ws_rows) * zs::BOOT_SLOTS * sizeof(unsigned long long), st));
+    ctx->epoch = 1;
+  }
+  if (pl.sync_window > 0) {   // before the cast kernel, so that cast -> fused kernel stay adjacent
+    const size_t n_cnt = static_cast<size_t>(pl.max_iters) * pl.windows_per_unit;
+    ZS_CUDA(cudaMemsetAsync(ctx->sync_cnt, 0, n_cnt * sizeof(unsigned int), st));
+  }
+
+  zs::SimTopkParams p{};
+  p.Q = static_cast<int>(Q);
+  p.n_bank = static_cast<int>(ctx->bank_rows);
+  p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
+  p.num_m_tiles = pl.m_tiles;
+  p.num_n_tiles = pl.n_tiles;
+  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.num_chunks = pl.chunks;
+  p.k = k_pass;
+  p.self_index = reinterpret_cast<const long long*>(self_index);
+  p.index_offset = index_offset;
+  p.part_scores = ctx->part_scores;
+  p.part_idx = ctx->part_idx;
+  p.dump = nullptr;
+  p.err_flag = ctx->err_flag;
+  p.trace = ctx->trace;
+  const char* share_env = getenv("ZSAAC_SHARE_THR");   // tuning hook: 0 = every unit warms up alone
+  p.row_thr = (share_env && share_env[0] == '0') ? nullptr : ctx->row_thr;
+  p.epoch = ctx->epoch;
+  const int n_lists = pl.chunks * zs::EPI_HALVES;
+  if (ctx->boot_enabled && p.row_thr != nullptr && bound_scores == nullptr && n_lists >= k_pass) {
+    p.boot = ctx->boot;
+    p.boot_slots = std::min(n_lists, zs::BOOT_SLOTS);
+  }
+  if (bound_scores != nullptr) {
+    p.bound_scores = bound_scores;
+    p.bound_idx = reinterpret_cast<const long long*>(bound_idx);
+    p.bound_stride = out_stride;
+  }
+  if (pl.sync_window > 0) {
+    p.sync_cnt = ctx->sync_cnt;
+    p.sync_window = pl.sync_window;
+    p.windows_per_unit = pl.windows_per_unit;
+    p.max_iters = pl.max_iters;
+  }
+  p.q_ws = ctx->q_ws;
+  p.q_pad = static_cast<int>(q_pad);
+  p.d = ctx->bank_d;
+
+  CUtensorMap qmap;
+  int rc = encode_rows_map(ctx, &qmap, ctx->q_ws, q_pad, ctx->bank_d, zs::BLOCK_M);
+  if (rc) return rc;
+
+  if (solo) {
+    p.solo = 1;
+    p.q_src = cast_queries ? queries : nullptr;
+    p.q_src_bf16 = (q_dtype == ZS_BF16) ? 1 : 0;
+    p.q_normalize = normalize;
+    p.grid_cnt = ctx->grid_cnt;
+    p.cast_target = ctx->cnt_base[0] + (cast_queries ? pl.ctas : 0);
+    p.done_target = ctx->cnt_base[1] + pl.ctas;
+    p.out_scores = out_scores;
+    p.out_idx = reinterpret_cast<long long*>(out_indices);
+    p.out_stride = out_stride;
+    rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
+                      : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+    if (rc == ZS_OK) {
+      ctx->solo_state = 1;
+      ctx->cnt_base[0] = p.cast_target;
+      ctx->cnt_base[1] = p.done_target;
+      return ZS_OK;
+    }
+    if (rc != ZS_ERR_STATE) return rc;
+    ctx->solo_state = -1;        // cooperative launch refused: three launches from now on
+    p.solo = 0;
+    p.q_src = nullptr;
+    p.grid_cnt = nullptr;
+    p.out_scores = nullptr;
+    p.out_idx = nullptr;
+  }
+
+  if (cast_queries) {
+    if (q_dtype == ZS_F32)
+      launch_normalize<float>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
+    else
+      launch_normalize<__nv_bfloat16>(queries, ctx->q_ws, Q, q_pad, ctx->bank_d, normalize, st);
+    ZS_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  // programmatic dependent launch: cast kernel -> fused kernel -> merge (not while profiling,
+  // the timing events would sit between the kernels)
+  ctx->pdl_next = cast_queries && ctx->pdl_enabled && !ctx->profiling;
+  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
+                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  ctx->pdl_next = false;
+  if (rc) return rc;
+  ZS_CUDA(launch_merge<int>(ctx->part_scores, ctx->part_idx, n_lists, Q * k_pass, Q * k_pass, Q, k_pass,
+                            index_offset, out_scores, reinterpret_cast<long long*>(out_indices), out_stride,
+                            /*pdl=*/ctx->pdl_enabled && !ctx->profiling, st));
+  ctx->launches += 1;
+  return ZS_OK;
+}
+
+}  // namespace
+
 int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, int normalize_queries,
               const int64_t* self_index, int64_t index_offset, float* out_scores,
               int64_t* out_indices, void* stream) {
   if (!ctx) return fail(ZS_ERR_INVALID, "zs_search: ctx is null");
+  ZS_CHECK_KERNEL_FLAG(ctx, "zs_search");
   if (!ctx->bank) return fail(ZS_ERR_STATE, "zs_search: no bank uploaded");
   if (Q < 0 || Q > 0x7fffff00ll) return fail(ZS_ERR_INVALID, "zs_search: Q=%lld", (long long)Q);
   if (q_dtype != ZS_F32 && q_dtype != ZS_BF16)
@@ -567,53 +757,20 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   if (!aligned16(queries)) return fail(ZS_ERR_INVALID, "zs_search: queries must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = ensure_workspace(ctx, Q, k);
+  const int k_first = std::min(k, (int)ZS_PASS_K);
+  int rc = ensure_workspace(ctx, Q, k_first);
   if (rc) return rc;
-  const Plan pl = make_plan(ctx, Q, k);
-  if (pl.sync_window > 0) {   // before the cast kernel, so that cast -> fused kernel stay adjacent
-    const size_t n_cnt = static_cast<size_t>(pl.max_iters) * pl.windows_per_unit;
-    ZS_CUDA(cudaMemsetAsync(ctx->sync_cnt, 0, n_cnt * sizeof(unsigned int), st));
+  const Plan pl = make_plan(ctx, Q, k_first);
+  // k <= 32: one pass.  k > 32: passes of 32; pass p continues strictly after the last element
+  // pass p-1 wrote (read from the caller's output arrays, where the merge has just put it).
+  for (int done = 0; done < k; done += ZS_PASS_K) {
+    const int k_pass = std::min(k - done, (int)ZS_PASS_K);
+    const float* bs = done ? out_scores + (done - 1) : nullptr;
+    const int64_t* bi = done ? out_indices + (done - 1) : nullptr;
+    rc = search_pass(ctx, queries, Q, q_dtype, k_pass, normalize_queries, /*cast_queries=*/done == 0,
+                     self_index, index_offset, bs, bi, out_scores + done, out_indices + done, k, pl, st);
+    if (rc) return rc;
   }
-  CUtensorMap qmap;
-  rc = prepare_queries(ctx, queries, Q, q_dtype, normalize_queries, &qmap, st);
-  if (rc) return rc;
-
-  zs::SimTopkParams p{};
-  p.Q = static_cast<int>(Q);
-  p.n_bank = static_cast<int>(ctx->bank_rows);
-  p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
-  p.num_m_tiles = pl.m_tiles;
-  p.num_n_tiles = pl.n_tiles;
-  p.tiles_per_chunk = pl.tiles_per_chunk;
-  p.num_chunks = pl.chunks;
-  p.k = k;
-  p.self_index = reinterpret_cast<const long long*>(self_index);
-  p.index_offset = index_offset;
-  p.part_scores = ctx->part_scores;
-  p.part_idx = ctx->part_idx;
-  p.dump = nullptr;
-  p.err_flag = ctx->err_flag;
-  p.trace = ctx->trace;
-  const char* share_env = getenv("ZSAAC_SHARE_THR");   // tuning hook: 0 = every unit warms up alone
-  p.row_thr = (share_env && share_env[0] == '0') ? nullptr : ctx->row_thr;
-  if (pl.sync_window > 0) {
-    p.sync_cnt = ctx->sync_cnt;
-    p.sync_window = pl.sync_window;
-    p.windows_per_unit = pl.windows_per_unit;
-    p.max_iters = pl.max_iters;
-  }
-  // programmatic dependent launch: cast kernel -> fused kernel -> merge (not while profiling,
-  // the timing events would sit between the kernels)
-  ctx->pdl_next = ctx->pdl_enabled && !ctx->profiling;
-  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
-                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
-  ctx->pdl_next = false;
-  if (rc) return rc;
-
-  ZS_CUDA(launch_merge<int>(ctx->part_scores, ctx->part_idx, pl.chunks * zs::EPI_HALVES, Q * k, Q * k,
-                            Q, k, index_offset, out_scores, reinterpret_cast<long long*>(out_indices),
-                            /*pdl=*/ctx->pdl_enabled && !ctx->profiling, st));
-  ctx->launches += 1;
   return ZS_OK;
 }
 
@@ -621,6 +778,7 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
                   const int64_t* target_index, int n_targets, int64_t index_offset,
                   float* out_target_scores, int64_t* out_ranks, void* stream) {
   if (!ctx) return fail(ZS_ERR_INVALID, "zs_rank_count: ctx is null");
+  ZS_CHECK_KERNEL_FLAG(ctx, "zs_rank_count");
   if (!ctx->bank) return fail(ZS_ERR_STATE, "zs_rank_count: no bank uploaded");
   if (Q < 0 || Q > 0x7fffff00ll) return fail(ZS_ERR_INVALID, "zs_rank_count: Q=%lld", (long long)Q);
   if (n_targets < 1 || n_targets > ZS_MAX_TARGETS)
@@ -760,7 +918,7 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ZS_CUDA(launch_merge<long long>(scores, reinterpret_cast<const long long*>(indices), S, score_stride,
                                   index_stride, Q, k, 0ll, out_scores,
-                                  reinterpret_cast<long long*>(out_indices), /*pdl=*/false, st));
+                                  reinterpret_cast<long long*>(out_indices), k, /*pdl=*/false, st));
   ctx->launches += 1;
   return ZS_OK;
 }
@@ -782,9 +940,12 @@ int zs_rescore_f32(zs_ctx* ctx, const float* queries, int64_t Q, int normalize, 
     return fail(ZS_ERR_INVALID, "zs_rescore_f32: queries and bank must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  zs::rescore_f32_kernel<<<static_cast<unsigned>(Q), zs::RESCORE_THREADS, 0, st>>>(
+  int P = 2;
+  while (P < kc) P <<= 1;
+  const size_t smem = static_cast<size_t>(P) * (sizeof(long long) + sizeof(float));   // <= 24 KiB
+  zs::rescore_f32_kernel<<<static_cast<unsigned>(Q), zs::RESCORE_THREADS, smem, st>>>(
       queries, bank, n_rows, d, normalize, reinterpret_cast<const long long*>(candidates), kc, k,
-      index_offset, out_scores, reinterpret_cast<long long*>(out_indices));
+      index_offset, out_scores, reinterpret_cast<long long*>(out_indices), P);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ZS_OK;
@@ -822,9 +983,93 @@ int zs_normalize_rows_f32(zs_ctx* ctx, const float* in, float* out, int64_t n_ro
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t blocks = (n_rows * 32 + 255) / 256;
-  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, n_rows, d, 1, nullptr);
+  zs::normalize_cast_kernel<float, float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n_rows, n_rows, d, 1);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
+  return ZS_OK;
+}
+
+namespace {
+
+constexpr int64_t kExactMaxScores = 1ll << 30;    // 4 GiB of fp32 scores
+
+int exact_prepare(zs_ctx* ctx, const char* fn, const float* queries, int64_t Q, const float* bank,
+                  int64_t n_rows, int d) {
+  if (Q < 0 || n_rows < 1) return fail(ZS_ERR_INVALID, "%s: Q=%lld n_rows=%lld", fn, (long long)Q, (long long)n_rows);
+  if (d < 4 || d % 4 != 0) return fail(ZS_ERR_INVALID, "%s: d=%d must be a multiple of 4", fn, d);
+  if (Q > 0x7fffff00ll || Q * n_rows > kExactMaxScores)
+    return fail(ZS_ERR_INVALID, "%s: %lld x %lld scores exceed the fp32 scratch limit; this entry point "
+                "is for small banks (use zs_search / zs_rank_count)", fn, (long long)Q, (long long)n_rows);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !bank) return fail(ZS_ERR_INVALID, "%s: null pointer", fn);
+  if (!aligned16(queries) || !aligned16(bank))
+    return fail(ZS_ERR_INVALID, "%s: queries and bank must be 16-byte aligned", fn);
+  if (Q * n_rows > ctx->exact_elems) {
+    if (ctx->exact_scores) { ZS_CUDA(cudaFree(ctx->exact_scores)); ctx->exact_scores = nullptr; ctx->exact_elems = 0; }
+    ZS_CUDA(cudaMalloc(&ctx->exact_scores, static_cast<size_t>(Q * n_rows) * sizeof(float)));
+    ctx->exact_elems = Q * n_rows;
+  }
+  if (!ctx->exact_counter) {
+    ZS_CUDA(cudaMalloc(&ctx->exact_counter, sizeof(unsigned int)));
+    ZS_CUDA(cudaMemset(ctx->exact_counter, 0, sizeof(unsigned int)));
+  }
+  return ZS_OK;
+}
+
+}  // namespace
+
+int zs_exact_topk_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, int normalize, int k, const int64_t* self_index, int64_t index_offset,
+                      float* out_scores, int64_t* out_indices, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_exact_topk_f32: ctx is null");
+  const int64_t avail = n_rows - (self_index ? 1 : 0);
+  if (k < 1 || k > avail)
+    return fail(ZS_ERR_INVALID, "zs_exact_topk_f32: selected index k out of range (k=%d, bank rows=%lld%s)",
+                k, (long long)n_rows, self_index ? " minus the excluded row" : "");
+  DeviceGuard guard(ctx->device);
+  int rc = exact_prepare(ctx, "zs_exact_topk_f32", queries, Q, bank, n_rows, d);
+  if (rc || Q == 0) return rc;
+  if (!out_scores || !out_indices) return fail(ZS_ERR_INVALID, "zs_exact_topk_f32: null output pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((n_rows + zs::EXACT_ROWS_PER_BLOCK - 1) / zs::EXACT_ROWS_PER_BLOCK);
+  const bool fused = Q <= zs::EXACT_FUSED_MAX_Q;     // one launch: the last block selects
+  zs::exact_scores_kernel<<<blocks, zs::EXACT_THREADS, 0, st>>>(
+      queries, static_cast<int>(Q), bank, n_rows, d, normalize, ctx->exact_scores, ctx->exact_counter,
+      fused ? k : 0, reinterpret_cast<const long long*>(self_index), index_offset, out_scores,
+      reinterpret_cast<long long*>(out_indices));
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  if (!fused) {
+    zs::exact_topk_kernel<<<static_cast<unsigned>((Q * 32 + 255) / 256), 256, 0, st>>>(
+        ctx->exact_scores, static_cast<int>(Q), n_rows, k, reinterpret_cast<const long long*>(self_index),
+        index_offset, out_scores, reinterpret_cast<long long*>(out_indices));
+    ZS_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return ZS_OK;
+}
+
+int zs_exact_rank_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                      int d, int normalize, const int64_t* target_index, int n_targets,
+                      int64_t index_offset, float* out_target_scores, int64_t* out_ranks, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_exact_rank_f32: ctx is null");
+  if (n_targets < 1) return fail(ZS_ERR_INVALID, "zs_exact_rank_f32: n_targets=%d", n_targets);
+  DeviceGuard guard(ctx->device);
+  int rc = exact_prepare(ctx, "zs_exact_rank_f32", queries, Q, bank, n_rows, d);
+  if (rc || Q == 0) return rc;
+  if (!target_index || !out_ranks) return fail(ZS_ERR_INVALID, "zs_exact_rank_f32: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((n_rows + zs::EXACT_ROWS_PER_BLOCK - 1) / zs::EXACT_ROWS_PER_BLOCK);
+  zs::exact_scores_kernel<<<blocks, zs::EXACT_THREADS, 0, st>>>(
+      queries, static_cast<int>(Q), bank, n_rows, d, normalize, ctx->exact_scores, ctx->exact_counter, 0,
+      nullptr, 0ll, nullptr, nullptr);
+  ZS_CUDA(cudaGetLastError());
+  const int64_t n_pairs = Q * n_targets;
+  zs::exact_rank_kernel<<<static_cast<unsigned>((n_pairs * 32 + 255) / 256), 256, 0, st>>>(
+      ctx->exact_scores, static_cast<int>(Q), n_rows, reinterpret_cast<const long long*>(target_index),
+      n_targets, index_offset, out_target_scores, reinterpret_cast<long long*>(out_ranks));
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 2;
   return ZS_OK;
 }
 

@@ -14,19 +14,13 @@ from typing import List, Sequence
 import torch
 
 from . import _abi
-from .retrieval import RelatedBank, _require_cuda, _stream_ptr
+from .retrieval import RelatedBank, _require_cuda, _stream_ptr, helper_context
 
 TEMPERATURE = 100.0   # predict_prompt.py:26  `(sim*100).softmax(dim=-1)`
 
-_HELPER = {}
-
-
 def _helper(device: torch.device) -> RelatedBank:
     """A context for the bank-less entry points (normalise, memory projection) on `device`."""
-    key = (device.type, device.index)
-    if key not in _HELPER:
-        _HELPER[key] = RelatedBank(1, 64, device=device)
-    return _HELPER[key]
+    return helper_context(device)
 
 
 def map2memory(audio_embed: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:

@@ -159,12 +159,8 @@ def load_data(raw_path: Union[str, Sequence[str]]) -> Tuple[torch.Tensor, List[d
 
 def _register_bank(bank: torch.Tensor, rb: RelatedBank) -> None:
     """Let process_data find the bf16 copy load_data already built for this tensor."""
-    import weakref
     from . import retrieval
-    key = (bank.data_ptr(), tuple(bank.shape), bank.dtype, str(bank.device), bank._version, True)
-    if len(retrieval._BANK_CACHE) >= retrieval._BANK_CACHE_MAX:
-        retrieval._BANK_CACHE.pop(next(iter(retrieval._BANK_CACHE)))[1].close()
-    retrieval._BANK_CACHE[key] = (weakref.ref(bank), rb)
+    retrieval._cache_insert(retrieval._cache_key(bank, True), bank, rb)
 
 
 def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnumber: int,

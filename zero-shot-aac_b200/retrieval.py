@@ -62,9 +62,16 @@ class RelatedBank:
         self.index_offset = int(index_offset)
         handle = ctypes.c_void_p()
         _abi.check(self._lib.zs_create(ctypes.byref(handle), dev.index))
-        self._ctx = handle
+        self._handle = handle
         self._finalizer = weakref.finalize(self, self._lib.zs_destroy, handle)
         _abi.check(self._lib.zs_bank_alloc(self._ctx, self.rows, self.dim))
+
+    @property
+    def _ctx(self) -> ctypes.c_void_p:
+        """The native context; raises once the bank has been closed (never a dangling pointer)."""
+        if self._handle is None:
+            raise RuntimeError("this RelatedBank has been closed")
+        return self._handle
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -175,7 +182,7 @@ class RelatedBank:
         """Re-score search candidates in fp32 and keep the k best (score desc, index asc).
 
         queries [Q, d] float32 (raw), bank_f32 [N, d] float32 on this device, candidates [Q, kc]
-        int64 global indices (kc <= 32; bank_f32 row 0 has global index `index_offset`).  With
+        int64 global indices (kc <= 2048; bank_f32 row 0 has global index `index_offset`).  With
         normalize=True the score is the cosine similarity computed entirely in fp32 — the
         arithmetic of the reference's torch.cosine_similarity (embeddings_related_generator.py:22)
         — so searching for k + margin candidates and re-scoring them removes the bf16 near-tie
@@ -301,42 +308,154 @@ class RelatedBank:
         return int(self._lib.zs_launch_count(self._ctx))
 
     def close(self) -> None:
+        """Destroy the native context now.  Every later call on this object raises."""
+        self._handle = None
         self._finalizer()
+
+    @property
+    def closed(self) -> bool:
+        return self._handle is None
 
 
 # ------------------------------------------------------------------------------------------------
 # Bank cache: process_data / sound_effect_choice receive the fp32 bank tensor on every call, as
 # in the reference; the bf16 copy is rebuilt only when that tensor (identity, version) changes.
+# The cache only ever DROPS its reference to an evicted RelatedBank: a caller (e.g. a suspended
+# process_data generator) may still hold the object, and the native context is destroyed by the
+# object's finalizer once the last reference is gone — never under a live user.
 _BANK_CACHE: "dict[tuple, tuple]" = {}   # key -> (weakref to the source tensor, RelatedBank)
 _BANK_CACHE_MAX = 4
+_REBUILDS = {"count": 0, "warned": False}
+
+
+def _cache_key(bank: torch.Tensor, normalize: bool) -> tuple:
+    return (bank.data_ptr(), tuple(bank.shape), bank.dtype, str(bank.device), bank._version,
+            bool(normalize))
+
+
+def _cache_insert(key: tuple, bank: torch.Tensor, obj: RelatedBank) -> None:
+    for stale in [k for k, (ref, _) in _BANK_CACHE.items() if ref() is None]:
+        _BANK_CACHE.pop(stale)               # the source tensor is gone: nobody can hit this entry
+    while len(_BANK_CACHE) >= _BANK_CACHE_MAX:
+        _BANK_CACHE.pop(next(iter(_BANK_CACHE)))
+    _BANK_CACHE[key] = (weakref.ref(bank), obj)
 
 
 def bank_for(bank: torch.Tensor, *, normalize: bool) -> RelatedBank:
-    key = (bank.data_ptr(), tuple(bank.shape), bank.dtype, str(bank.device), bank._version,
-           bool(normalize))
+    key = _cache_key(bank, normalize)
     hit = _BANK_CACHE.get(key)
-    if hit is not None and hit[0]() is bank:
+    if hit is not None and hit[0]() is bank and not hit[1].closed:
         return hit[1]
     if hit is not None:                      # same address, different tensor object: stale
-        _BANK_CACHE.pop(key)[1].close()
+        _BANK_CACHE.pop(key)
     obj = RelatedBank.from_tensor(bank, normalize=normalize)
-    if len(_BANK_CACHE) >= _BANK_CACHE_MAX:
-        _BANK_CACHE.pop(next(iter(_BANK_CACHE)))[1].close()
-    _BANK_CACHE[key] = (weakref.ref(bank), obj)
+    _REBUILDS["count"] += 1
+    if _REBUILDS["count"] > 64 and not _REBUILDS["warned"]:
+        import warnings
+        _REBUILDS["warned"] = True
+        warnings.warn("zsaac_b200: the bf16 search copy of the bank has been rebuilt more than 64 "
+                      "times; pass the SAME bank tensor object on every call (a fresh temporary "
+                      "such as `bank.cuda()` defeats the cache), or hold a RelatedBank yourself")
+    _cache_insert(key, bank, obj)
     return obj
 
 
 def clear_bank_cache() -> None:
-    while _BANK_CACHE:
-        _BANK_CACHE.popitem()[1][1].close()
+    _BANK_CACHE.clear()
 
 
-RESCORE_MARGIN = 8      # extra candidates fetched for fp32 re-scoring (k + margin <= 32)
+# ------------------------------------------------------------------------------------------------
+# Exact fp32 path for small banks (label banks, zero-shot prompts, retrieval metrics): the
+# reference computes these with a plain fp32 matmul, so the mirror does too — on the GPU, through
+# zs_exact_topk_f32 / zs_exact_rank_f32 — instead of ranking bf16 products.
+EXACT_MAX_BANK_ROWS = 65536          # beyond this the tensor-core search (+ fp32 re-scoring) takes over
+EXACT_MAX_SCORES = 1 << 28           # Q * N fp32 scores of scratch (1 GiB)
+
+_HELPERS: "dict[tuple, RelatedBank]" = {}
+
+
+def helper_context(device: torch.device) -> RelatedBank:
+    """A context for the bank-less entry points (normalise, exact fp32, memory projection)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    h = _HELPERS.get(key)
+    if h is None or h.closed:
+        h = RelatedBank(1, 64, device=torch.device("cuda", key[1]))
+        _HELPERS[key] = h
+    return h
+
+
+def exact_fits(n_queries: int, n_rows: int) -> bool:
+    return n_rows <= EXACT_MAX_BANK_ROWS and n_queries * n_rows <= EXACT_MAX_SCORES
+
+
+def _f32_on(x: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def exact_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, normalize: bool = False,
+               self_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 scores (raw dot product, or cosine with normalize=True) of queries [Q, d] against a
+    small bank [N, d] and the k best per query under (score desc, index asc).  One launch for up
+    to 64 queries.  Returns (float32 [Q, k], int64 [Q, k]) on the bank's CUDA device."""
+    _require_cuda()
+    dev = bank.device if bank.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    b = _f32_on(bank, dev)
+    q = _f32_on(queries, dev)
+    if q.dim() != 2 or b.dim() != 2 or q.shape[1] != b.shape[1]:
+        raise ValueError(f"exact_topk expects queries [Q, d] and bank [N, d], got {tuple(q.shape)} "
+                         f"and {tuple(b.shape)}")
+    k = int(k)
+    nq = q.shape[0]
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    self_ptr = None
+    if self_index is not None:
+        self_index = self_index.detach().to(device=dev, dtype=torch.int64).contiguous()
+        self_ptr = self_index.data_ptr()
+    h = helper_context(dev)
+    with torch.cuda.device(dev):
+        _abi.check(h._lib.zs_exact_topk_f32(
+            h._ctx, q.data_ptr(), nq, b.data_ptr(), b.shape[0], b.shape[1], 1 if normalize else 0, k,
+            self_ptr, 0, out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(dev)))
+    for t in (q, b):
+        t.record_stream(torch.cuda.current_stream(dev))
+    return out_s, out_i
+
+
+def exact_rank(queries: torch.Tensor, bank: torch.Tensor, targets: torch.Tensor, *,
+               normalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Position of bank rows `targets` [Q, T] (int64, < 0 = unused) in every query's fp32
+    similarity ordering (score desc, index asc): (ranks int64 [Q, T], target scores fp32 [Q, T])."""
+    _require_cuda()
+    dev = bank.device if bank.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    b = _f32_on(bank, dev)
+    q = _f32_on(queries, dev)
+    t = targets.detach().to(device=dev, dtype=torch.int64)
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    t = t.contiguous()
+    if q.dim() != 2 or b.dim() != 2 or q.shape[1] != b.shape[1] or t.shape[0] != q.shape[0]:
+        raise ValueError("exact_rank expects queries [Q, d], bank [N, d], targets [Q, T]")
+    ranks = torch.empty(t.shape, dtype=torch.int64, device=dev)
+    scores = torch.empty(t.shape, dtype=torch.float32, device=dev)
+    h = helper_context(dev)
+    with torch.cuda.device(dev):
+        _abi.check(h._lib.zs_exact_rank_f32(
+            h._ctx, q.data_ptr(), q.shape[0], b.data_ptr(), b.shape[0], b.shape[1],
+            1 if normalize else 0, t.data_ptr(), t.shape[1], 0, scores.data_ptr(), ranks.data_ptr(),
+            _stream_ptr(dev)))
+    for x in (q, b, t):
+        x.record_stream(torch.cuda.current_stream(dev))
+    return ranks, scores
+
+
+RESCORE_MARGIN = 8      # extra candidates fetched for fp32 re-scoring
 
 
 def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_self: bool = False,
                  self_index: Optional[torch.Tensor] = None, normalize: bool = True,
-                 rescore_fp32: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                 rescore_fp32: bool = False, precision: str = "bf16"
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """scores, indices = top-k of cosine_similarity(queries, bank).
 
     queries [Q, d], bank [N, d] (float32 or bfloat16).  With normalize=True both sides are
@@ -345,9 +464,24 @@ def related_topk(queries: torch.Tensor, bank: torch.Tensor, k: int, *, exclude_s
     exclude_self=True drops bank row i from the result of query i (self_index defaults to
     arange(Q)); the reference itself never excludes (slot 0 of its output is the item).
     rescore_fp32=True re-scores k + 8 bf16 candidates in fp32 from `bank` (float32 inputs only).
+    precision="fp32" ranks exact fp32 scores on CUDA cores instead (small banks only: N <= 65,536
+    and Q * N <= 2^28); the default "bf16" is the fused tensor-core search.  k may exceed 32: the
+    search then runs ceil(k / 32) passes over the bank (k <= 1024).
     Returns float32 [Q, k] scores (descending) and int64 [Q, k] bank indices on the GPU.
     """
     _require_cuda()
+    if precision not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    if precision == "fp32":
+        q2 = queries.detach()
+        if q2.dim() == 1:
+            q2 = q2.unsqueeze(0)
+        if not exact_fits(q2.shape[0], bank.shape[0]):
+            raise ValueError("precision='fp32' is for small banks (N <= 65,536, Q * N <= 2^28); "
+                             "use rescore_fp32=True on the tensor-core search instead")
+        if exclude_self and self_index is None:
+            self_index = torch.arange(q2.shape[0], dtype=torch.int64)
+        return exact_topk(q2, bank, k, normalize=normalize, self_index=self_index)
     rb = bank_for(bank, normalize=normalize)   # a CPU bank is copied to the current GPU once
     q = queries.detach()
     if q.dim() == 1:
@@ -370,6 +504,7 @@ def search_rescored(rb: RelatedBank, queries: torch.Tensor, bank_f32: torch.Tens
         raise TypeError("rescore_fp32 needs float32 queries and a float32 bank")
     bank_dev = bank_f32 if bank_f32.device == rb.device else bank_f32.to(rb.device)
     avail = rb.rows - (1 if self_index is not None else 0)
+    # (the margin only shrinks where the bank, or ZS_MAX_K = 1024, leaves no room for it)
     kc = max(int(k), min(int(k) + RESCORE_MARGIN, _abi.ZS_MAX_K, avail))
     _, cand = rb.search(queries, kc, normalize_queries=normalize, self_index=self_index)
     return rb.rescore(queries, bank_dev, cand, k, normalize=normalize, index_offset=rb.index_offset)

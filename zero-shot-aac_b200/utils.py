@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from .retrieval import _require_cuda, bank_for
+from .retrieval import (_require_cuda, bank_for, exact_fits, exact_topk, search_rescored)
 
 
 def sound_effect_choice(prefix, sound_effect_embeddings, choice_num):
@@ -19,16 +19,27 @@ def sound_effect_choice(prefix, sound_effect_embeddings, choice_num):
     retrieval/models/ase_model.py:54,59).  Returns an int64 CPU tensor of shape
     prefix.shape[:-1] + (choice_num,), like the reference.
 
-    The similarity + top-k run on the GPU through libzsaac_b200 for CPU and CUDA inputs alike
-    (CPU tensors are copied to the current device; the label bank is converted once and cached).
+    The label bank is small (L = 527 AudioSet labels), so the scores are computed in fp32 like the
+    reference's own matmul (zs_exact_topk_f32: one launch for up to 64 prefixes; the indices equal
+    the reference's except at fp32 rounding ties).  A bank too large for that route goes through
+    the tensor-core search with fp32 re-scoring.  CPU inputs are copied to the current device.
     There is no CPU fallback: inside a forked DataLoader worker, where CUDA cannot be initialised,
-    this raises — call it from the main process / collate step instead.
+    this raises — batch the call in the collate step of the main process instead
+    (zsaac_b200.dataset.collate_with_sound_effects, INTEGRATION.md).
     """
     _require_cuda()
-    rb = bank_for(sound_effect_embeddings, normalize=False)
     lead = tuple(prefix.shape[:-1])
-    q = prefix.detach().reshape(-1, prefix.shape[-1]).to(rb.device)
-    if q.dtype not in (torch.float32, torch.bfloat16):
-        q = q.float()
-    _, index = rb.search(q, int(choice_num), normalize_queries=False)
-    return index.reshape(*lead, int(choice_num)).cpu()
+    q = prefix.detach().reshape(-1, prefix.shape[-1])
+    k = int(choice_num)
+    if exact_fits(q.shape[0], sound_effect_embeddings.shape[0]):
+        _, index = exact_topk(q, sound_effect_embeddings, k, normalize=False)
+    else:
+        rb = bank_for(sound_effect_embeddings, normalize=False)
+        q = q.to(rb.device)
+        if q.dtype == torch.float32 and sound_effect_embeddings.dtype == torch.float32:
+            _, index = search_rescored(rb, q, sound_effect_embeddings, k, normalize=False)
+        else:
+            if q.dtype not in (torch.float32, torch.bfloat16):
+                q = q.float()
+            _, index = rb.search(q, k, normalize_queries=False)
+    return index.reshape(*lead, k).cpu()
