@@ -5,10 +5,20 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A step is ONE pass of the hot path over one batch of synthetic queries: normalise + cast ->
-fused cosine-similarity/top-k against the bank (row-sharded over the N ranks) -> all-gather of the
-shard-local top-k -> k-way merge.  Default workload: BASELINE.json config 4 (65,536 queries vs a
+fused cosine-similarity/top-k against the bank (row-sharded over the N ranks) -> exchange of the
+shard-local top-k -> k-way merge.  Headline workload: BASELINE.json config 4 (65,536 queries vs a
 10 M-row bf16 bank, d=1024, top-32), the configuration its metric ("... at 1/2/4/8 B200") is
 quoted on; the bank is fixed as N grows (strong scaling).  Rank 0 prints ONE JSON line.
+
+Before anything is timed the run verifies itself (`parity_gate`, SURVEY §8d "correctness gate"):
+sampled queries are re-scored in fp32 against the whole (sharded) bank and north_star's rule is
+applied (|score - fp32| <= 1e-3; every returned index within 1e-3 of the fp32 k-th score; every
+clear fp32 winner returned); at N > 1 the merged result must be bit-identical on every rank and
+bit-identical to a single-GPU search of a 4,096-query slice.  A failed gate aborts non-zero.
+After the headline the other named shapes are timed as well (`workloads`): BASELINE configs
+1, 2, 3, 5 and the HBM-bound batches Q in {1, 32, 128} against the 400 k and 10 M banks, each with
+its own gate and roofline, next to the unfused library strawman (torch.matmul bf16 + topk) and
+the reference's literal per-item loop.
 
 --impl reference times the reference's CPU formulation of the same path (torch fp32:
 F.normalize(q) @ bank.T -> topk, all host threads) on a bounded sample of the workload.
@@ -36,9 +46,11 @@ WORKLOADS = {
     "allpairs_400k": (400_000, 400_000, 5, True, 105, 203),      # configs[4]
 }
 DEFAULT_WORKLOAD = "synthetic_10m"
+SMALL_Q = (1, 32, 128)      # HBM-bound batches, k = 10
 BANK_BLOCK = 65536          # rows per generation block; seed = bank_seed * 2**32 + block id
 L2_BYTES = 126 << 20        # B200 L2 capacity
-REBALANCE_DEFAULT = False
+GATE_SAMPLES = 64
+GATE_TOL = 1e-3             # north_star: scores within 1e-3 of fp32, index sets equal except near-ties
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -120,8 +132,9 @@ def gen_queries(torch, Q: int, seed: int, device="cpu"):
     return torch.randn(Q, D, generator=g) if device == "cpu" else torch.randn(Q, D, generator=g).to(device)
 
 
-def fill_shard(torch, bank, lo: int, hi: int, bank_seed: int, device):
-    """Generate global bank rows [lo, hi) block by block (identical for every world size)."""
+def bank_rows_fp32(torch, device, bank_seed: int, lo: int, hi: int):
+    """Yield (first global row, fp32 rows) covering global bank rows [lo, hi) block by block —
+    identical for every world size (per-block seeds)."""
     row = lo
     while row < hi:
         block = row // BANK_BLOCK
@@ -129,9 +142,207 @@ def fill_shard(torch, bank, lo: int, hi: int, bank_seed: int, device):
         rows = gen_bank_block(torch, device, bank_seed, block, BANK_BLOCK)
         take_lo = row - b_lo
         take_hi = min(hi - b_lo, BANK_BLOCK)
-        bank.upload(rows[take_lo:take_hi], row - lo, normalize=True)
+        yield row, rows[take_lo:take_hi]
         row = b_lo + take_hi
+
+
+def fill_shard(torch, bank, lo: int, hi: int, bank_seed: int, device):
+    for row, rows in bank_rows_fp32(torch, device, bank_seed, lo, hi):
+        bank.upload(rows, row - lo, normalize=True)
     torch.cuda.synchronize(device)
+
+
+def make_queries(torch, name: str, Q: int, device):
+    """(pinned host queries, device queries, self_index) of a workload."""
+    _, _, _, excl, q_seed, bank_seed = WORKLOADS[name]
+    if excl:
+        # BASELINE config 5: queries are the bank rows themselves after the reference's
+        # noise_injection (utils.py:19-31: normalise, add N(0, 0.001 I), renormalise in search)
+        q_dev = torch.empty(Q, D, device=device)
+        gq = torch.Generator(device=device).manual_seed(q_seed)
+        for blk in range(-(-Q // BANK_BLOCK)):
+            r0, r1 = blk * BANK_BLOCK, min((blk + 1) * BANK_BLOCK, Q)
+            rows = torch.nn.functional.normalize(gen_bank_block(torch, device, bank_seed, blk, BANK_BLOCK)[:r1 - r0], dim=-1)
+            q_dev[r0:r1] = rows + torch.randn(r1 - r0, D, device=device, generator=gq) * (0.001 ** 0.5)
+        q_host = q_dev.cpu().pin_memory()
+        self_index = torch.arange(Q, dtype=torch.int64, device=device)
+    else:
+        q_host = gen_queries(torch, Q, q_seed).pin_memory()
+        q_dev = q_host.to(device, non_blocking=True)
+        self_index = None
+    return q_host, q_dev, self_index
+
+
+# ------------------------------------------------------------------------------------------------
+def parity_gate(torch, dist, world, device, lo, hi, bank_seed, q_dev, self_index, k, result):
+    """fp32 re-scoring of sampled queries against this rank's shard (regenerated block by block
+    from the same seeds), reduced over ranks, compared with the merged result by north_star's rule."""
+    Q = q_dev.shape[0]
+    sel = torch.unique(torch.linspace(0, Q - 1, min(Q, GATE_SAMPLES), device=device).round().long())
+    ns = sel.numel()
+    got_s, got_i = result[0][sel], result[1][sel]
+    qn = torch.nn.functional.normalize(q_dev[sel].float(), dim=-1)
+    self_sel = self_index[sel] if self_index is not None else None
+    top_s = torch.full((ns, k), float("-inf"), device=device)
+    top_i = torch.full((ns, k), -1, dtype=torch.int64, device=device)
+    ret_fp32 = torch.full((ns, k), float("-inf"), device=device)
+    for row0, rows in bank_rows_fp32(torch, device, bank_seed, lo, hi):
+        s = qn @ torch.nn.functional.normalize(rows, dim=-1).T           # fp32 (TF32 off by default)
+        n = rows.shape[0]
+        inside = (got_i >= row0) & (got_i < row0 + n)
+        ret_fp32 = torch.where(inside, s.gather(1, (got_i - row0).clamp(0, n - 1)), ret_fp32)
+        if self_sel is not None:
+            mine = (self_sel >= row0) & (self_sel < row0 + n)
+            s[mine.nonzero().squeeze(1), (self_sel[mine] - row0)] = float("-inf")
+        bs, bi = torch.topk(s, min(k, n), dim=1)
+        cat_s, cat_i = torch.cat([top_s, bs], dim=1), torch.cat([top_i, bi + row0], dim=1)
+        top_s, order = torch.topk(cat_s, k, dim=1)
+        top_i = cat_i.gather(1, order)
+    if world > 1:
+        all_s = [torch.empty_like(top_s) for _ in range(world)]
+        all_i = [torch.empty_like(top_i) for _ in range(world)]
+        dist.all_gather(all_s, top_s)
+        dist.all_gather(all_i, top_i)
+        cat_s, cat_i = torch.cat(all_s, dim=1), torch.cat(all_i, dim=1)
+        top_s, order = torch.topk(cat_s, k, dim=1)
+        top_i = cat_i.gather(1, order)
+        dist.all_reduce(ret_fp32, op=dist.ReduceOp.MAX)
+    kth = top_s[:, k - 1:k]
+    score_err = (got_s - ret_fp32).abs().max().item()
+    below = int((ret_fp32 < kth - GATE_TOL).sum().item())               # returned, but not a near-winner
+    clear = top_s > kth + GATE_TOL                                      # must be returned
+    present = (top_i.unsqueeze(2) == got_i.unsqueeze(1)).any(dim=2)
+    missing = int((clear & ~present).sum().item())
+    ordered = bool((got_s[:, :-1] >= got_s[:, 1:]).all().item()) if k > 1 else True
+    no_self = True if self_sel is None else not bool((got_i == self_sel[:, None]).any().item())
+    exact_match = float((got_i == top_i).float().mean().item())
+    ok = score_err <= GATE_TOL and below == 0 and missing == 0 and ordered and no_self
+    return {"sampled_queries": ns, "max_abs_score_err_vs_fp32": score_err, "returned_below_band": below,
+            "clear_winners_missing": missing, "sorted": ordered, "self_excluded": no_self,
+            "index_agreement_with_fp32": exact_match, "ok": bool(ok)}
+
+
+def rank_consistency_gate(torch, dist, zs, world, rank, device, N, bank_seed, q_dev, self_index, k, result,
+                          single_gpu=True):
+    """N > 1: the merged result must be the same bits on every rank, and the same bits a single
+    GPU holding the whole bank returns for a 4,096-query slice."""
+    out = {}
+    ref_s, ref_i = result[0].clone(), result[1].clone()
+    dist.broadcast(ref_s, 0)
+    dist.broadcast(ref_i, 0)
+    same = torch.tensor([int(torch.equal(ref_s, result[0]) and torch.equal(ref_i, result[1]))], device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out["identical_on_all_ranks"] = bool(same.item())
+    if not single_gpu:
+        out["ok"] = out["identical_on_all_ranks"]
+        return out
+    flag = torch.ones(1, device=device, dtype=torch.int64)
+    n_slice = min(4096, q_dev.shape[0])
+    if rank == 0:
+        whole = zs.RelatedBank(N, D, device=device)
+        fill_shard(torch, whole, 0, N, bank_seed, device)
+        si = self_index[:n_slice] if self_index is not None else None
+        s1, i1 = whole.search(q_dev[:n_slice], k, self_index=si)
+        torch.cuda.synchronize(device)
+        flag[0] = int(torch.equal(s1, result[0][:n_slice]) and torch.equal(i1, result[1][:n_slice]))
+        whole.close()
+        del whole
+        torch.cuda.empty_cache()
+    dist.broadcast(flag, 0)
+    out["single_gpu_slice_queries"] = n_slice
+    out["bit_identical_to_single_gpu"] = bool(flag.item())
+    out["ok"] = out["identical_on_all_ranks"] and out["bit_identical_to_single_gpu"]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def roofline_of(peaks, peaks_src, Q, shard_rows, k, k_ms, long_step):
+    flop = 2.0 * Q * shard_rows * D
+    bytes_alg = 2.0 * shard_rows * D + Q * D * 2.0 + Q * k * 12.0
+    t_tensor_burst = flop / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
+    if t_tensor_burst >= t_hbm:
+        peak = peaks["bf16_tflops_sustained"] if long_step else peaks["bf16_tflops"]
+        achieved = flop / (k_ms * 1e-3) / 1e12
+        r = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+             "peak_kind": f"{'sustained' if long_step else 'burst'} bf16, {peaks_src}",
+             "frac_of_burst": achieved / peaks["bf16_tflops"]}
+    else:
+        gbs = bytes_alg / (k_ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": gbs / peaks["hbm_gbs"], "peak_kind": f"copy bandwidth, {peaks_src}"}
+    r["kernel"] = "zs_simtopk_kernel"
+    r["kernel_ms"] = k_ms
+    return r
+
+
+class Timer:
+    """Event-timed steps: back to back when a step's inputs exceed L2, else an event pair per step
+    with a 256 MB write in between (L2 flush).  Max over ranks."""
+
+    def __init__(self, torch, dist, world, device):
+        self.torch, self.dist, self.world, self.device = torch, dist, world, device
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def run(self, fn, steps, flush_l2, finish=None):
+        torch = self.torch
+        self.barrier()
+        if not flush_l2:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            if finish is not None:
+                finish()
+            e1.record()
+            self.barrier()
+            total = e0.elapsed_time(e1)
+        else:
+            if self.flush_buf is None:
+                self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+            pairs = []
+            for _ in range(steps):
+                self.flush_buf.zero_()                 # evicts bank, queries and outputs from L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                if finish is not None:
+                    finish()
+                e1.record()
+                pairs.append((e0, e1))
+            self.barrier()
+            total = sum(a.elapsed_time(b) for a, b in pairs)
+        ms = torch.tensor([total], device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
+
+
+def strawman_topk(torch, q_bf16, bank_bf16, k, q_chunk=1024, n_chunk=1_000_000):
+    """The best unfused library formulation on the same GPU: torch.matmul (bf16 in, fp32 out) +
+    torch.topk, chunked so that the score block fits."""
+    out_s, out_i = [], []
+    for q0 in range(0, q_bf16.shape[0], q_chunk):
+        qc = q_bf16[q0:q0 + q_chunk]
+        best_s = best_i = None
+        for n0 in range(0, bank_bf16.shape[0], n_chunk):
+            s = torch.matmul(qc, bank_bf16[n0:n0 + n_chunk].T).float()
+            ts, ti = torch.topk(s, min(k, s.shape[1]), dim=1)
+            ti = ti + n0
+            if best_s is None:
+                best_s, best_i = ts, ti
+            else:
+                cs, ci = torch.cat([best_s, ts], 1), torch.cat([best_i, ti], 1)
+                best_s, order = torch.topk(cs, k, dim=1)
+                best_i = ci.gather(1, order)
+        out_s.append(best_s)
+        out_i.append(best_i)
+    return torch.cat(out_s), torch.cat(out_i)
 
 
 class CpuReference:
@@ -160,6 +371,17 @@ class CpuReference:
         t0 = time.perf_counter()
         self.oracle.fast_topk(self.queries, self.bank, self.k)
         return time.perf_counter() - t0
+
+    def literal_loop(self, n_items: int) -> dict:
+        """The reference's process_data exactly as written (one query per iteration,
+        embeddings_related_generator.py:19-28; oracle.process_data_literal) on `n_items` items."""
+        items = [{"text_embedding": self.queries[i:i + 1].clone()} for i in range(n_items)]
+        t0 = time.perf_counter()
+        n = sum(1 for _ in self.oracle.process_data_literal(self.bank, items, self.k))
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "queries/s", "kind": "port", "cores": int(self.torch.get_num_threads()),
+                "sample": f"literal per-item loop (normalize -> cosine_similarity -> topk({self.k}) -> gather) "
+                          f"on {n} items x {self.n_s} bank rows, {dt:.2f} s"}
 
     def baseline(self, dt: float) -> dict:
         scale = self.n_s / self.N
@@ -211,11 +433,92 @@ def run_reference(args):
     return 0
 
 
+class Workload:
+    """One named shape, bank resident (row-sharded at N > 1), queries resident and pinned."""
+
+    def __init__(self, env, name, Q=None, N=None, k=None, bank=None, label=None):
+        torch, zs = env["torch"], env["zs"]
+        wQ, wN, wk, excl, _, bank_seed = WORKLOADS[name]
+        self.env, self.name = env, name
+        self.Q, self.N, self.k = Q or wQ, N or wN, k or wk
+        self.excl, self.bank_seed = excl, bank_seed
+        self.label = label or name
+        world, device = env["world"], env["device"]
+        if bank is not None:
+            self.bank, self.owns_bank = bank, False
+        else:
+            self.owns_bank = True
+            if world > 1:
+                from zsaac_b200.sharded import ShardedRelatedBank
+                self.bank = ShardedRelatedBank(self.N, D, device=device)
+            else:
+                self.bank = zs.RelatedBank(self.N, D, device=device)
+        self.local = self.bank.local if world > 1 else self.bank
+        self.lo, self.hi = (self.bank.lo, self.bank.hi) if world > 1 else (0, self.N)
+        if self.owns_bank:
+            fill_shard(torch, self.local, self.lo, self.hi, bank_seed, device)
+        self.q_host, self.q_dev, self.self_index = make_queries(torch, name, self.Q, device)
+        self.local.reserve(self.Q, self.k)
+        shard_bytes = (self.hi - self.lo) * D * 2 + self.Q * D * 4
+        self.flush_l2 = shard_bytes < 2 * L2_BYTES
+
+    def search(self):
+        return self.bank.search(self.q_dev, self.k, self_index=self.self_index)
+
+    def gate(self):
+        env = self.env
+        torch, dist = env["torch"], env["dist"]
+        res = self.search()
+        torch.cuda.synchronize(env["device"])
+        g = parity_gate(torch, dist, env["world"], env["device"], self.lo, self.hi, self.bank_seed,
+                        self.q_dev, self.self_index, self.k, res)
+        if env["world"] > 1:
+            # (the single-GPU comparison needs the whole bank on rank 0: done once per bank, by its owner)
+            g["ranks"] = rank_consistency_gate(torch, dist, env["zs"], env["world"], env["rank"], env["device"],
+                                               self.N, self.bank_seed, self.q_dev, self.self_index,
+                                               self.k, res, single_gpu=self.owns_bank)
+            g["ok"] = bool(g["ok"] and g["ranks"]["ok"])
+        return g
+
+    def close(self):
+        if self.owns_bank:
+            self.local.close()
+
+
+def describe(w: Workload) -> str:
+    return (f"{w.label}: {w.Q} queries vs {w.N}-row bank, d={D}, top-{w.k}"
+            + (", self-exclusion" if w.excl else ""))
+
+
+def time_side_workload(env, w: Workload, steps: int):
+    """Gate + device-resident timing of one of the extra shapes -> dict for `workloads`."""
+    torch, timer, peaks, peaks_src = env["torch"], env["timer"], env["peaks"], env["peaks_src"]
+    gate = w.gate()
+    for _ in range(3):
+        w.search()
+    launches0 = w.local.launch_count
+    w.local.profile(True)
+    total = timer.run(w.search, steps, w.flush_l2)
+    kernel_ms = w.local.kernel_times_ms()
+    w.local.profile(False)
+    launches = (w.local.launch_count - launches0) / steps
+    ms = total / steps
+    k_ms = statistics.mean(kernel_ms) if kernel_ms else ms
+    roof = roofline_of(peaks, peaks_src, w.Q, w.hi - w.lo, w.k, k_ms, long_step=False)
+    roof["kernel_share_of_step"] = k_ms / ms
+    # whole search (every launch of it, launch gaps included) against the same roofline
+    whole = roofline_of(peaks, peaks_src, w.Q, w.hi - w.lo, w.k, ms, long_step=False)
+    return {"workload": describe(w), "ms_per_step": ms, "value": w.Q / (ms * 1e-3), "unit": "queries/s",
+            "steps": steps, "l2": "flushed between steps" if w.flush_l2 else "inputs larger than L2",
+            "launches_per_search": launches, "plan_chunks_tiles_ctas": list(w.local.plan(w.Q, w.k)),
+            "roofline": roof, "search_frac_of_roofline": whole["frac"], "parity_gate": gate}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import zsaac_b200
-    from zsaac_b200.sharded import ShardedRelatedBank
+    from zsaac_b200.sharded import SearchPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,222 +534,209 @@ def run_ours(args):
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-
-    name = args.workload
-    Q, N, k, excl, q_seed, bank_seed = WORKLOADS[name]
-    if args.queries:
-        Q = args.queries
-    if args.bank_rows:
-        N = args.bank_rows
     peaks, peaks_src = load_peaks()
+    timer = Timer(torch, dist, world, device)
+    env = {"torch": torch, "dist": dist, "zs": zsaac_b200, "world": world, "rank": rank, "device": device,
+           "peaks": peaks, "peaks_src": peaks_src, "timer": timer}
+    steps = args.steps
+    warmup = max(args.warmup, 3)
 
-    # ---- bank: resident in HBM as bf16 before anything is timed
-    if world > 1:
-        bank = ShardedRelatedBank(N, D, device=device)
-        lo, hi = bank.lo, bank.hi
-        local = bank.local
-    else:
-        local = zsaac_b200.RelatedBank(N, D, device=device)
-        bank = local
-        lo, hi = 0, N
-    fill_shard(torch, local, lo, hi, bank_seed, device)
+    # ---- headline workload: bank resident in HBM as bf16 before anything is timed
+    head = Workload(env, args.workload, Q=args.queries or None, N=args.bank_rows or None)
+    Q, N, k = head.Q, head.N, head.k
+    local, bank = head.local, head.bank
 
-    # ---- N > 1: size the shards by the measured speed of each GPU (untimed calibration).  Every
-    # step ends in an all-gather, so the slowest GPU sets the pace, and the GPUs of one box differ
-    # by several per cent under the power cap (kernel_ms_per_rank).  Two calibration searches on
-    # equal shards give rows/ms per rank; if the ranks differ by more than 2 % the bank is
-    # re-sharded in proportion (ShardedRelatedBank(shard_weights=...)) and refilled.
-    shard_weights = None
-    if world > 1 and args.rebalance:
-        qc = gen_queries(torch, Q, q_seed).to(device)
-        local.reserve(Q, k)
-        for _ in range(2):
-            bank.search(qc, k)
-        torch.cuda.synchronize(device)
-        local.profile(True)
-        for _ in range(2):
-            bank.search(qc, k)
-        torch.cuda.synchronize(device)
-        t_cal = statistics.mean(local.kernel_times_ms())
-        local.profile(False)
-        speeds = torch.zeros(world, device=device, dtype=torch.float64)
-        speeds[rank] = (hi - lo) / t_cal
-        dist.all_reduce(speeds, op=dist.ReduceOp.SUM)
-        speeds = speeds.tolist()
-        if max(speeds) / min(speeds) > 1.02:
-            shard_weights = [round(v / max(speeds), 4) for v in speeds]
-            local.close()
-            del bank, local
-            torch.cuda.empty_cache()
-            bank = ShardedRelatedBank(N, D, device=device, shard_weights=shard_weights)
-            lo, hi = bank.lo, bank.hi
-            local = bank.local
-            fill_shard(torch, local, lo, hi, bank_seed, device)
-        del qc
+    # ---- untimed: the run verifies itself first
+    gate = head.gate()
+    if not gate["ok"]:
+        if rank == 0:
+            print(json.dumps({"parity_gate": gate, "error": "parity gate failed; nothing was timed"}), flush=True)
+        return 3
 
-    if excl:
-        # BASELINE config 5: queries are the bank rows themselves after the reference's
-        # noise_injection (utils.py:19-31: normalise, add N(0, 0.001 I), renormalise in search)
-        q_dev = torch.empty(Q, D, device=device)
-        gq = torch.Generator(device=device).manual_seed(q_seed)
-        for blk in range(-(-Q // BANK_BLOCK)):
-            r0, r1 = blk * BANK_BLOCK, min((blk + 1) * BANK_BLOCK, Q)
-            rows = torch.nn.functional.normalize(gen_bank_block(torch, device, bank_seed, blk, BANK_BLOCK)[:r1 - r0], dim=-1)
-            q_dev[r0:r1] = rows + torch.randn(r1 - r0, D, device=device, generator=gq) * (0.001 ** 0.5)
-        q_host = q_dev.cpu().pin_memory()
-    else:
-        q_host = gen_queries(torch, Q, q_seed).pin_memory()
-        q_dev = q_host.to(device, non_blocking=True)
-    self_index = torch.arange(Q, dtype=torch.int64, device=device) if excl else None
-    local.reserve(Q, k)
-    out_host_s = torch.empty(Q, k, dtype=torch.float32).pin_memory()
-    out_host_i = torch.empty(Q, k, dtype=torch.int64).pin_memory()
+    # ---- timed region 1: inputs resident in HBM (value).  N > 1: the exchange + merge of step i
+    # runs on a side stream under the fused kernel of step i+1 (SearchPipeline).
+    pipe = SearchPipeline(bank, Q, k, depth=2, from_host=False, to_host=False, result="replicated",
+                          self_index=head.self_index) if world > 1 else None
 
     def step_device():
-        return bank.search(q_dev, k, self_index=self_index)
-
-    def step_e2e():
-        # N > 1: every rank uploads 1/N of the host batch and the slices are all-gathered over
-        # NVLink (ShardedRelatedBank.replicate_from_host) instead of N full PCIe copies
-        qd = bank.replicate_from_host(q_host) if world > 1 else q_host.to(device, non_blocking=True)
-        s, i = bank.search(qd, k, self_index=self_index)
-        out_host_s.copy_(s, non_blocking=True)
-        out_host_i.copy_(i, non_blocking=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
-    # Timing rule: either the inputs of a step exceed the L2 (126 MB) or the L2 is flushed between
-    # timed steps.  Small workloads (configs 1-2: the bf16 bank alone fits in L2) take the second
-    # route: every step is bracketed by its own event pair and a 256 MB write runs in between.
-    shard_bytes = (hi - lo) * D * 2 + Q * D * 4
-    flush_l2 = shard_bytes < 2 * L2_BYTES
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush_l2 else None
-
-    def timed(fn, steps):
-        barrier()
-        if not flush_l2:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                fn()
-            e1.record()
-            barrier()
-            total = e0.elapsed_time(e1)
+        if pipe is not None:
+            pipe.submit(head.q_dev)
         else:
-            pairs = []
-            for _ in range(steps):
-                flush_buf.zero_()                     # evicts bank, queries and outputs from L2
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                fn()
-                e1.record()
-                pairs.append((e0, e1))
-            barrier()
-            total = sum(a.elapsed_time(b) for a, b in pairs)
-        ms = torch.tensor([total], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+            head.search()
 
-    for _ in range(max(args.warmup, 3)):
+    finish_device = pipe.wait_stream if pipe is not None else None
+    for _ in range(warmup):
         step_device()
+    if pipe is not None:
+        pipe.wait_stream()
     torch.cuda.synchronize(device)
-
-    # ---- timed region 1: inputs resident in HBM (value) -------------------------------------
     launches0 = local.launch_count
     local.profile(True)
     with ClockSampler(local_rank) as clocks:
-        total_ms = timed(step_device, args.steps)
+        total_ms = timer.run(step_device, steps, head.flush_l2, finish=finish_device)
     kernel_ms = local.kernel_times_ms()
     local.profile(False)
     launches = local.launch_count - launches0
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     value = Q / (ms_per_step * 1e-3)
 
-    # ---- timed region 2: host buffers in, host buffers out (e2e) -----------------------------
+    # ---- timed region 2: host buffers in, host buffers out (e2e).  Every rank uploads 1/N of the
+    # pinned host batch (all-gathered over NVLink) and reads back 1/N of the merged rows; upload,
+    # search and exchange/merge/read-back of consecutive steps overlap on three streams.
+    e2e_pipe = SearchPipeline(bank, Q, k, depth=2, from_host=True, to_host=True, result="row_slice",
+                              self_index=head.self_index)
+
+    last_slot = [0]
+
+    def step_e2e():
+        last_slot[0] = e2e_pipe.submit(head.q_host)
+
     for _ in range(2):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_pipe.wait_stream()
+    torch.cuda.synchronize(device)
+    # the read-back of the e2e path is checked against the device-resident result (untimed)
+    r_lo, r_hi = e2e_pipe.out_rows
+    ref_s, ref_i = head.search()
+    torch.cuda.synchronize(device)
+    hs, hi_ = e2e_pipe.result_of(last_slot[0], host=True)
+    e2e_ok = torch.equal(hs, ref_s[r_lo:r_hi].cpu()) and torch.equal(hi_, ref_i[r_lo:r_hi].cpu())
+    flag = torch.tensor([int(e2e_ok)], device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    gate["e2e_readback_identical"] = bool(flag.item())
+    if not gate["e2e_readback_identical"]:
+        if rank == 0:
+            print(json.dumps({"parity_gate": gate, "error": "e2e read-back differs from the device result"}), flush=True)
+        return 3
+    e2e_ms = timer.run(step_e2e, steps, head.flush_l2, finish=e2e_pipe.wait_stream) / steps
     e2e_value = Q / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (this rank's shard) ---------------------------------
-    shard_rows = hi - lo
-    flop = 2.0 * Q * shard_rows * D
+    shard_rows = head.hi - head.lo
     k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
-    achieved_tf = flop / (k_ms * 1e-3) / 1e12
-    ai = Q                                           # flop per bank byte ~ Q (bank dominates bytes)
-    ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    # which measured peak applies: the sustained one when the timed region ran power-capped (long
-    # back-to-back tensor work), the burst one for short kernels at full clocks
     clock_report = clocks.report()
     capped = ("sw_power_cap" in clock_report["reasons"] and clock_report["sm_mhz"] is not None
               and clock_report["sm_max_mhz"] and clock_report["sm_mhz"] < 0.85 * clock_report["sm_max_mhz"])
-    long_step = capped or total_ms > 1000.0
-    if ai >= ridge:
-        peak = peaks["bf16_tflops_sustained"] if long_step else peaks["bf16_tflops"]
-        roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved_tf / peak,
-                    "peak_kind": f"{'sustained' if long_step else 'burst'} bf16, {peaks_src}",
-                    "frac_of_burst": achieved_tf / peaks["bf16_tflops"]}
-    else:
-        bytes_alg = 2.0 * shard_rows * D + Q * D * 2.0 + Q * k * 12.0
-        gbs = bytes_alg / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": gbs / peaks["hbm_gbs"], "peak_kind": f"copy bandwidth, {peaks_src}"}
-    roofline["kernel"] = "zs_simtopk_kernel"
-    roofline["kernel_ms"] = k_ms
+    roofline = roofline_of(peaks, peaks_src, Q, shard_rows, k, k_ms, long_step=capped or total_ms > 1000.0)
     if world > 1:
-        # every step ends in an all-gather, so the slowest rank's kernel sets the step time
+        # every step ends in an exchange, so the slowest rank's kernel sets the step time
         per_rank = torch.zeros(world, device=device)
         per_rank[rank] = k_ms
         dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
         roofline["kernel_ms_per_rank"] = [round(v, 3) for v in per_rank.tolist()]
+        roofline["step_tail_ms_beyond_slowest_kernel"] = round(ms_per_step - max(per_rank.tolist()), 3)
     roofline["kernel_share_of_step"] = k_ms / ms_per_step
-    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     roofline["traffic"] = None
     try:
         if world == 1:          # captured with ncu on one GPU holding the whole bank
-            with open(traffic_path) as f:
-                roofline["traffic"] = json.load(f).get(name)
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                roofline["traffic"] = json.load(f).get(head.name)
     except Exception:
         pass
 
+    # ---- the other named shapes (each gated, then timed; all sharded the same way at N > 1) ------
+    workloads = []
+    if not args.headline_only:
+        side_steps = max(3, min(steps, 20))
+        for q_small in SMALL_Q:                                  # HBM-bound batches vs the resident bank
+            w = Workload(env, head.name, Q=q_small, k=10, bank=bank, label=f"{head.name}_q{q_small}")
+            workloads.append(time_side_workload(env, w, side_steps))
+        for name in ("clotho_eval", "audiocaps", "wavcaps_400k", "allpairs_400k"):
+            if name == head.name:
+                continue
+            w = Workload(env, name)
+            workloads.append(time_side_workload(env, w, 3 if name == "allpairs_400k" else side_steps))
+            if name == "wavcaps_400k":
+                for q_small in SMALL_Q:
+                    ws = Workload(env, name, Q=q_small, k=10, bank=w.bank, label=f"{name}_q{q_small}")
+                    workloads.append(time_side_workload(env, ws, side_steps))
+                if world == 1:      # unfused library strawman on the same GPU, same operands
+                    bank_bf16 = torch.empty(w.N, D, dtype=torch.bfloat16, device=device)
+                    for row0, rows in bank_rows_fp32(torch, device, w.bank_seed, 0, w.N):
+                        bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
+                    q_bf16 = torch.nn.functional.normalize(w.q_dev, dim=-1).bfloat16()
+
+                    def straw():
+                        return strawman_topk(torch, q_bf16, bank_bf16, w.k)
+
+                    for _ in range(2):
+                        straw()
+                    st_ms = timer.run(straw, 3, False) / 3
+                    workloads[-1 - len(SMALL_Q)]["strawman_torch_matmul_bf16_topk_ms"] = st_ms
+                    del bank_bf16, q_bf16
+            w.close()
+            del w
+            torch.cuda.empty_cache()
+        if world == 1 and head.name == "synthetic_10m":
+            # strawman on a sample of the headline (the [Q, N] fp32 score block does not fit otherwise)
+            n_q = 1024
+            bank_bf16 = torch.empty(N, D, dtype=torch.bfloat16, device=device)
+            for row0, rows in bank_rows_fp32(torch, device, head.bank_seed, 0, N):
+                bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
+            q_bf16 = torch.nn.functional.normalize(head.q_dev[:n_q], dim=-1).bfloat16()
+            strawman_topk(torch, q_bf16, bank_bf16, k)
+            st_ms = timer.run(lambda: strawman_topk(torch, q_bf16, bank_bf16, k), 2, False) / 2
+            ours_ms = timer.run(lambda: bank.search(head.q_dev[:n_q], k), 5, False) / 5
+            workloads.append({"workload": f"{head.name} sample: {n_q} queries vs {N}-row bank, top-{k}",
+                              "ms_per_step": ours_ms, "value": n_q / (ours_ms * 1e-3), "unit": "queries/s",
+                              "strawman_torch_matmul_bf16_topk_ms": st_ms})
+            del bank_bf16, q_bf16
+            torch.cuda.empty_cache()
+
     cpu_baseline = None
+    literal = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        ref = CpuReference(torch, name)
+        ref = CpuReference(torch, head.name)
         cpu_baseline = ref.baseline(min(ref.one_pass() for _ in range(3)))
+        if not args.headline_only:
+            # the reference's literal loop on config 1: CPU port, and on this GPU as written
+            ref1 = CpuReference(torch, "clotho_eval")
+            literal = {"cpu": ref1.literal_loop(128)}
+            from oracle import oracle
+            bank_cuda = ref1.bank.to(device)
+            items = [{"text_embedding": ref1.queries[i:i + 1].clone()} for i in range(ref1.q_s)]
+            sum(1 for _ in oracle.process_data_literal(bank_cuda, items[:16], ref1.k, device="cuda"))   # warm-up
+            t0 = time.perf_counter()
+            n = sum(1 for _ in oracle.process_data_literal(bank_cuda, items, ref1.k, device="cuda"))
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+            literal["torch_cuda_as_written"] = {"value": n / dt, "unit": "queries/s",
+                                                "sample": f"{n} items x {ref1.n_s} rows, {dt:.2f} s, torch CUDA fp32"}
 
     if rank == 0:
         plan = local.plan(Q, k)
         line = {
             "metric": "related-caption retrieval queries/s (top-k, d=1024)",
-            "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"{name}: {Q} queries vs {N}-row bank, d={D}, top-{k}"
-                            + (", self-exclusion" if excl else ""),
-                "parallelism": f"bank row-sharded over {world} GPU(s), queries replicated, "
-                               "all-gather + k-way merge" if world > 1 else "single GPU",
-                "bank_rows_per_gpu": shard_rows, "shard_weights": shard_weights,
+                "workload": describe(head),
+                "parallelism": (f"bank row-sharded over {world} GPUs, queries replicated, all-gather + k-way "
+                                "merge on a side stream under the next step's kernel") if world > 1 else "single GPU",
+                "bank_rows_per_gpu": shard_rows,
                 "bank_dtype": "bf16", "accumulate": "fp32",
                 "l2": ("L2 flushed between timed steps (256 MB write); bank shard %.0f MB + queries "
-                       "%.0f MB per step" % (shard_rows * D * 2 / 1e6, Q * D * 4 / 1e6)) if flush_l2
+                       "%.0f MB per step" % (shard_rows * D * 2 / 1e6, Q * D * 4 / 1e6)) if head.flush_l2
                       else ("inputs larger than L2: bank shard %.1f GB + queries %.0f MB per step"
                             % (shard_rows * D * 2 / 1e9, Q * D * 4 / 1e6)),
                 "plan_chunks_tiles_ctas": list(plan),
                 "tflops": 2.0 * Q * N * D / (ms_per_step * 1e-3) / 1e12,
             },
+            "parity_gate": gate,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": world * Q * k * 12},
+                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
+                    "how": "pinned host queries in (1/N per rank, replicated over NVLink), merged rows out to "
+                           "pinned host memory (1/N of the rows per rank); upload / search / exchange+read-back "
+                           "of consecutive steps overlap on three streams"},
             "gpu_launches": int(launches) * world,
             "clocks": clock_report,
+            "workloads": workloads,
+            "literal_reference_loop_clotho_eval": literal,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -465,8 +755,8 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override the query count (smoke runs)")
     ap.add_argument("--bank-rows", type=int, default=0, help="override the bank rows (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rebalance", action=argparse.BooleanOptionalAction, default=REBALANCE_DEFAULT,
-                    help="N > 1: size the bank shards by the measured speed of each GPU")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the extra shapes / strawman / literal loop (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -195,9 +195,10 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 
 /* The same planner for a hypothetical device and bank (no context, no GPU needed): sm_count SMs,
  * bank_rows rows, cta_group 0 = choose per search, 1 / 2 = pinned.  lockstep_window receives the
- * bank tiles per lock-step window (0 = lock-step off for this shape).  For host-side tests. */
+ * bank tiles per lock-step window (0 = lock-step off for this shape), cta_group_chosen the CTA
+ * group the plan uses (1 = single CTAs, 2 = cta_group::2 pairs).  For host-side tests. */
 int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group, int* n_chunks,
-                int* tiles_per_chunk, int* n_ctas, int* lockstep_window);
+                int* tiles_per_chunk, int* n_ctas, int* lockstep_window, int* cta_group_chosen);
 
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t zs_launch_count(const zs_ctx* ctx);

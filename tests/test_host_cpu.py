@@ -258,10 +258,10 @@ def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
 
 def _plan_dry(sm, n, q, k, cg=0):
     lib = zsaac_b200.load_library()
-    a, b, c, w = (ctypes.c_int() for _ in range(4))
+    a, b, c, w, g = (ctypes.c_int() for _ in range(5))
     _abi.check(lib.zs_plan_dry(sm, n, q, k, cg, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
-                               ctypes.byref(w)))
-    return a.value, b.value, c.value, w.value
+                               ctypes.byref(w), ctypes.byref(g)))
+    return a.value, b.value, c.value, w.value, g.value
 
 
 def test_planner_invariants_and_baseline_plans(monkeypatch):
@@ -278,8 +278,10 @@ def test_planner_invariants_and_baseline_plans(monkeypatch):
         q = rng.choice([rng.randint(1, 300), rng.randint(300, 70_000), rng.randint(70_000, 500_000)])
         k = rng.randint(1, 32)
         cg = rng.choice([0, 1, 2])
-        chunks, tpc, ctas, window = _plan_dry(sm, n, q, k, cg)
-        group = cg if cg else (2 if q > 256 else 1)
+        chunks, tpc, ctas, window, group = _plan_dry(sm, n, q, k, cg)
+        assert group == cg if cg else group in (1, 2)
+        if not cg:   # one 128-row tile: single CTAs; large batches: pairs; in between: cost model
+            assert group == 1 if q <= 128 else (group == 2 if q > 2048 else True)
         n_tiles = -(-n // 256)
         m_tiles = -(-q // (128 * group))
         assert 1 <= chunks <= min(n_tiles, 256)                 # two column halves each: <= 512 lists
@@ -287,13 +289,14 @@ def test_planner_invariants_and_baseline_plans(monkeypatch):
         assert ctas % group == 0 and group <= ctas <= max(sm // group, 1) * group
         assert ctas // group == min(m_tiles * chunks, max(sm // group, 1))
         assert window in (0, 32) and (window == 0 or (m_tiles > 1 and tpc >= 4 * window))
-    pins = {(10_000_000, 65_536, 32): (13, 3005, 148, 32),      # config 4, one GPU
-            (1_250_000, 65_536, 32): (2, 2442, 148, 32),        # config 4, one rank of eight
-            (400_000, 8_192, 10): (16, 98, 148, 0),             # config 3
-            (400_000, 400_000, 5): (5, 313, 148, 32),           # config 5
-            (49_838, 975, 10): (18, 11, 144, 0),                # config 2
-            (19_195, 1_045, 5): (13, 6, 130, 0),                # config 1
-            (400_000, 128, 10): (143, 11, 143, 0)}              # HBM-bound small batch
+    pins = {(10_000_000, 65_536, 32): (13, 3005, 148, 32, 2),   # config 4, one GPU
+            (1_250_000, 65_536, 32): (2, 2442, 148, 32, 2),     # config 4, one rank of eight
+            (400_000, 8_192, 10): (16, 98, 148, 0, 2),          # config 3
+            (400_000, 400_000, 5): (5, 313, 148, 32, 2),        # config 5
+            (49_838, 975, 10): (18, 11, 144, 0, 2),             # config 2
+            (19_195, 1_045, 5): (15, 5, 135, 0, 1),             # config 1: 9 tiles of 128 rows beat 5 of 256
+            (400_000, 256, 10): (72, 22, 144, 0, 2),            # just above one tile: pairs
+            (400_000, 128, 10): (143, 11, 143, 0, 1)}           # HBM-bound small batch
     for (n, q, k), want in pins.items():
         assert _plan_dry(148, n, q, k) == want, (n, q, k)
     monkeypatch.setenv("ZSAAC_CHUNKS", "4")                      # tuning hook

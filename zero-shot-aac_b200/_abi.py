@@ -57,7 +57,7 @@ SIGNATURES = {
     "zs_plan": (_int, [_c_ctx, _i64, _int, ctypes.POINTER(_int), ctypes.POINTER(_int),
                        ctypes.POINTER(_int)]),
     "zs_plan_dry": (_int, [_int, _i64, _i64, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int),
-                           ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+                           ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "zs_launch_count": (_i64, [_c_ctx]),
     "zs_kernel_error": (_int, [_c_ctx]),
     "zs_profile_enable": (_int, [_c_ctx, _int]),

@@ -38,9 +38,12 @@ __device__ __forceinline__ bool ranks_before(float s, long long i, float ts, lon
 }
 
 // Top-k of one score row by one warp: k rounds; round r finds the best element that comes
-// strictly after the element chosen in round r-1, so no "taken" flags are needed.  Scores are
-// read through L2 (they may have been written by other blocks of the same launch).
-__device__ __forceinline__ void warp_topk_row(const float* row, int64_t n, int k, long long self_col,
+// strictly after the element chosen in round r-1, so no "taken" flags are needed.  `load(c)`
+// returns score c (from shared memory when the row has been staged there, else through L2: the
+// scores may have been written by other blocks of the same launch); loads are issued in
+// independent batches of 8 so that a round costs one memory round trip per 256 columns.
+template <typename Load>
+__device__ __forceinline__ void warp_topk_row(Load load, int64_t n, int k, long long self_col,
                                               long long index_offset, float* out_s, long long* out_i,
                                               int lane) {
   const long long SENT = 0x7fffffffffffffffll;
@@ -49,11 +52,21 @@ __device__ __forceinline__ void warp_topk_row(const float* row, int64_t n, int k
   for (int r = 0; r < k; ++r) {
     float best_s = -CUDART_INF_F;
     long long best_i = SENT;
-    for (int64_t c = lane; c < n; c += 32) {
-      const float s = __ldcg(row + c);
-      if (s != s || c == self_col) continue;                       // NaN never ranks
-      const bool after_last = (s < last_s) || (s == last_s && c > last_i);
-      if (after_last && ranks_before(s, c, best_s, best_i)) { best_s = s; best_i = c; }
+    for (int64_t c0 = lane; c0 < n; c0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t c = c0 + 32 * u;
+        v[u] = (c < n) ? load(c) : CUDART_NAN_F;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t c = c0 + 32 * u;
+        const float s = v[u];
+        const bool usable = (s == s) && c != self_col;                 // NaN never ranks
+        const bool after_last = (s < last_s) || (s == last_s && c > last_i);
+        if (usable && after_last && ranks_before(s, c, best_s, best_i)) { best_s = s; best_i = c; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -74,6 +87,8 @@ __device__ __forceinline__ void warp_topk_row(const float* row, int64_t n, int k
     last_i = best_i;
   }
 }
+
+constexpr int EXACT_STAGE_COLS = 1024;      // rows up to this long are staged in shared memory (per warp)
 
 __global__ void __launch_bounds__(EXACT_THREADS)
 exact_scores_kernel(const float* __restrict__ queries, int Q, const float* __restrict__ bank,
@@ -154,14 +169,25 @@ exact_scores_kernel(const float* __restrict__ queries, int Q, const float* __res
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  __shared__ float staged[EXACT_THREADS / 32][EXACT_STAGE_COLS];
   for (int q = warp; q < Q; q += EXACT_THREADS / 32) {
     long long self_col = -1;
     if (self_index != nullptr) {
       const long long g = self_index[q];
       if (g >= 0) self_col = g - index_offset;
     }
-    warp_topk_row(scores + static_cast<int64_t>(q) * n_bank, n_bank, k, self_col, index_offset,
-                  out_scores + static_cast<int64_t>(q) * k, out_idx + static_cast<int64_t>(q) * k, lane);
+    const float* row = scores + static_cast<int64_t>(q) * n_bank;
+    float* out_s = out_scores + static_cast<int64_t>(q) * k;
+    long long* out_i = out_idx + static_cast<int64_t>(q) * k;
+    if (n_bank <= EXACT_STAGE_COLS) {
+      float* mine = staged[warp];
+      for (int c = lane; c < n_bank; c += 32) mine[c] = __ldcg(row + c);   // one round trip, all loads in flight
+      __syncwarp();
+      warp_topk_row([&](int64_t c) { return mine[c]; }, n_bank, k, self_col, index_offset, out_s, out_i, lane);
+      __syncwarp();
+    } else {
+      warp_topk_row([&](int64_t c) { return __ldcg(row + c); }, n_bank, k, self_col, index_offset, out_s, out_i, lane);
+    }
   }
 }
 
@@ -178,7 +204,8 @@ exact_topk_kernel(const float* scores, int Q, int64_t n_bank, int k,
     const long long g = self_index[q];
     if (g >= 0) self_col = g - index_offset;
   }
-  warp_topk_row(scores + static_cast<int64_t>(q) * n_bank, n_bank, k, self_col, index_offset,
+  const float* row = scores + static_cast<int64_t>(q) * n_bank;
+  warp_topk_row([&](int64_t c) { return row[c]; }, n_bank, k, self_col, index_offset,
                 out_scores + static_cast<int64_t>(q) * k, out_idx + static_cast<int64_t>(q) * k, lane);
 }
 

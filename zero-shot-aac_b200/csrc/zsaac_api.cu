@@ -87,7 +87,7 @@ struct zs_ctx {
   unsigned long long cnt_base[2] = {0, 0};
   int solo_state = 0;                     // 0 = not probed, 1 = cooperative launch works, -1 = unavailable
   int solo_override = -1;                 // env ZSAAC_SOLO=0|1 (tests / A-B runs); -1 = choose per search
-  bool boot_enabled = true;               // env ZSAAC_BOOT=0 switches the threshold bootstrap off
+  int boot_override = -1;                 // env ZSAAC_BOOT=0|1: bootstrap off / on wherever it is valid; -1 = per search
   float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
   int64_t part_elems = 0;
@@ -145,24 +145,20 @@ int kcap_for(int k) {
 struct Plan {
   int cg, m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
   int sync_window, windows_per_unit, max_iters;   // lock-step of the bank stream (0 = off)
+  double cost;                                    // planner's estimate, in CG=2 bank-tile times
 };
 
 constexpr int kSyncWindowTiles = 32;   // 32 tiles x 512 KiB = 16 MiB of bank per window
 
-// CTA pairs (cta_group::2, 256-row query tiles, half the shared-memory fill per MMA) as soon as
-// the batch exceeds one 128-row tile: a single CTA would have to refill 768 KiB of operands per
-// bank tile (6.4 us at the ~120 GB/s one SM can pull from L2, against 4.3 us of MMA), a CTA of a
-// pair only 512 KiB.  A single 128-row tile streams the bank fastest from independent CTAs.
-int pick_cta_group(const zs_ctx* ctx, int64_t Q) {
-  if (ctx->cta_group_override) return ctx->cta_group_override;
-  return Q > zs::BLOCK_M ? 2 : 1;
-}
+// A single CTA (cta_group::1) has to pull 768 KiB of operands through shared memory per bank tile,
+// a CTA of a pair only 512 KiB, for the same 8192 cycles of MMA: measured 4-9 % more time per
+// tile (profiles/r02/bench_small_variants.jsonl).
+constexpr double kSingleCtaTileCost = 1.08;
 
 // Split the bank into `chunks` contiguous runs of 256-row tiles so that (query tiles x chunks)
 // work units fill the SMs in whole waves with the least padded work.
-Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
+Plan make_plan_for(const zs_ctx* ctx, int64_t Q, int k, int cg) {
   Plan pl{};
-  const int cg = pick_cta_group(ctx, Q);
   pl.cg = cg;
   const int workers = std::max(1, ctx->sm_count / cg);
   pl.m_tiles = static_cast<int>((Q + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
@@ -191,6 +187,7 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
   }
   pl.chunks = best_s;
   pl.tiles_per_chunk = (pl.n_tiles + best_s - 1) / best_s;
+  pl.cost = best_cost * (cg == 1 ? kSingleCtaTileCost : 1.0);
   const int64_t units = static_cast<int64_t>(pl.m_tiles) * pl.chunks;
   const int n_workers = static_cast<int>(std::min<int64_t>(units, workers));
   pl.ctas = n_workers * cg;
@@ -208,6 +205,19 @@ Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
     pl.max_iters = static_cast<int>((units + n_workers - 1) / n_workers);
   }
   return pl;
+}
+
+// One 128-row query tile streams the bank fastest from independent CTAs (an HBM-bound search).
+// Beyond that: CTA pairs (cta_group::2, 256-row query tiles) for large batches, where they run at
+// the MMA rate; for the few-tile batches in between whichever geometry the cost model prefers
+// (e.g. 1,045 queries are 9 tiles of 128 rows but 5 tiles of 256: 18 % padding for pairs).
+Plan make_plan(const zs_ctx* ctx, int64_t Q, int k) {
+  if (ctx->cta_group_override) return make_plan_for(ctx, Q, k, ctx->cta_group_override);
+  if (Q <= zs::BLOCK_M) return make_plan_for(ctx, Q, k, 1);
+  const Plan pair = make_plan_for(ctx, Q, k, 2);
+  if (Q > 16 * zs::BLOCK_M) return pair;
+  const Plan single = make_plan_for(ctx, Q, k, 1);
+  return single.cost < pair.cost ? single : pair;
 }
 
 // Query workspace rows are padded to whole 256-row tile pairs (zero rows), so the query-side TMA
@@ -422,7 +432,7 @@ int zs_create(zs_ctx** out, int device) {
   const char* solo = getenv("ZSAAC_SOLO");
   if (solo && (solo[0] == '0' || solo[0] == '1')) ctx->solo_override = solo[0] - '0';
   const char* boot = getenv("ZSAAC_BOOT");
-  if (boot && boot[0] == '0') ctx->boot_enabled = false;
+  if (boot && (boot[0] == '0' || boot[0] == '1')) ctx->boot_override = boot[0] - '0';
   int coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop)
     ctx->solo_state = -1;
@@ -547,7 +557,7 @@ int zs_plan(const zs_ctx* ctx, int64_t Q, int k, int* n_chunks, int* tiles_per_c
 }
 
 int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group, int* n_chunks,
-                int* tiles_per_chunk, int* n_ctas, int* lockstep_window) {
+                int* tiles_per_chunk, int* n_ctas, int* lockstep_window, int* cta_group_chosen) {
   if (sm_count < 1 || bank_rows < 1 || Q < 1 || k < 1 || k > ZS_MAX_K || cta_group < 0 || cta_group > 2)
     return fail(ZS_ERR_INVALID, "zs_plan_dry: sm_count=%d bank_rows=%lld Q=%lld k=%d cta_group=%d",
                 sm_count, (long long)bank_rows, (long long)Q, k, cta_group);
@@ -560,6 +570,7 @@ int zs_plan_dry(int sm_count, int64_t bank_rows, int64_t Q, int k, int cta_group
   if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
   if (n_ctas) *n_ctas = pl.ctas;
   if (lockstep_window) *lockstep_window = pl.sync_window;
+  if (cta_group_chosen) *cta_group_chosen = pl.cg;
   return ZS_OK;
 }
 
@@ -619,6 +630,11 @@ bool solo_wanted(zs_ctx* ctx, int64_t Q, const Plan& pl) {
   }
   if (pl.ctas > ctx->sm_count) return false;
   if (ctx->solo_override == 1) return true;
+  // One 128-row tile against a long bank is an HBM-bound stream: there three launches chained
+  // by programmatic dependent launch overlap the next search's prologue with this one's tail
+  // and win by ~10 % (profiles/r02/bench_small_variants.jsonl); everything else up to
+  // kSoloMaxQueries is faster, or as fast, as one cooperative launch.
+  if (pl.cg == 1 && pl.m_tiles == 1) return false;
   return Q <= kSoloMaxQueries;
 }
 
@@ -662,7 +678,10 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
   p.row_thr = (share_env && share_env[0] == '0') ? nullptr : ctx->row_thr;
   p.epoch = ctx->epoch;
   const int n_lists = pl.chunks * zs::EPI_HALVES;
-  if (ctx->boot_enabled && p.row_thr != nullptr && bound_scores == nullptr && n_lists >= k_pass) {
+  // (not for a single 128-row tile: that search is HBM-bound, its epilogue has slack anyway)
+  const bool hbm_stream = pl.cg == 1 && pl.m_tiles == 1;
+  if (ctx->boot_override != 0 && p.row_thr != nullptr && bound_scores == nullptr && n_lists >= k_pass &&
+      (!hbm_stream || ctx->boot_override == 1)) {
     p.boot = ctx->boot;
     p.boot_slots = std::min(n_lists, zs::BOOT_SLOTS);
   }

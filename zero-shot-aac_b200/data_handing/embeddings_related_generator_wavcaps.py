@@ -7,6 +7,7 @@ files; `--input_path` takes one or more paths, reference :45).
 import argparse
 
 from ..related_pipeline import load_data as _load_data
+from ..related_pipeline import add_extension_flags, run_cli
 from ..related_pipeline import process_data, save_data_to_hdf5  # noqa: F401  (re-exported)
 
 
@@ -24,16 +25,9 @@ def main(argv=None):
     parser.add_argument('--input_path', nargs='+', type=str)
     parser.add_argument('--output_path', type=str, help="output path files")
     parser.add_argument('--topnumber', type=int, default=5)
-    # extension (not in the reference): pickle the output records in N forked processes
-    parser.add_argument('--writer_procs', type=int, default=None)
-    # extension: pickle tensors through numpy (same objects after pickle.load, ~3x faster)
-    parser.add_argument('--fast_pickle', action='store_true', default=None)
+    add_extension_flags(parser)      # --gpus --exclude_self --[no-]rescore_fp32 --dtype --writer_procs --fast_pickle
     args = parser.parse_args(argv)
-    valid_text_embs, all_data = load_data(args.input_path)
-    processed_data_gen = process_data(valid_text_embs, all_data, args.topnumber)
-    total_items = len(all_data)
-    save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs,
-                      fast_pickle=args.fast_pickle)
+    run_cli(args, "zsaac_b200.data_handing.embeddings_related_generator_wavcaps", argv, load_data)
 
 
 if __name__ == '__main__':

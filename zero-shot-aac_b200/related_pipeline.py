@@ -17,7 +17,7 @@ from typing import Iterable, Iterator, List, Sequence, Tuple, Union
 
 import torch
 
-from .retrieval import RelatedBank, _require_cuda, bank_for, search_rescored
+from .retrieval import RelatedBank, _require_cuda, bank_for
 
 try:  # the reference wraps the writer loop in tqdm (embeddings_related_generator.py:33)
     from tqdm import tqdm
@@ -132,6 +132,22 @@ def _read_records(paths: Sequence[str]) -> List[dict]:
     return all_data
 
 
+def _dist_info():
+    """(torch.distributed module or None, rank, world) — multi-GPU mode is on when the script was
+    launched with one process per GPU (torchrun) and the process group is up."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def item_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of items rank `rank` processes (and writes) in multi-GPU mode: the rank
+    files concatenated in rank order are the single-GPU stream."""
+    per = -(-n_items // world)
+    return min(rank * per, n_items), min((rank + 1) * per, n_items)
+
+
 def load_data(raw_path: Union[str, Sequence[str]]) -> Tuple[torch.Tensor, List[dict]]:
     """(bank, all_data): bank = fp32 [N, d] unit rows on the GPU, all_data = the pickled records.
 
@@ -141,6 +157,8 @@ def load_data(raw_path: Union[str, Sequence[str]]) -> Tuple[torch.Tensor, List[d
     scrambles the order; here the bank keeps input order, which only affects how exact ties are
     ordered.  Val/test records carry `text_embedding: 0` (embeddings_generator.py:72) and fail
     here exactly as they do in the reference (int has no .cpu()).
+    In multi-GPU mode every rank reads the file(s) and holds the fp32 bank (rows are gathered and
+    re-scored from it); the bf16 search copy is built per shard by process_data.
     """
     _require_cuda()
     paths = [raw_path] if isinstance(raw_path, (str, bytes)) else list(raw_path)
@@ -148,8 +166,11 @@ def load_data(raw_path: Union[str, Sequence[str]]) -> Tuple[torch.Tensor, List[d
     all_captions = [raw_data["text_embedding"].cpu() for raw_data in all_data]      # :14
     host = torch.cat(all_captions, dim=0).to(torch.float32).contiguous().pin_memory()
     dev = host.to("cuda", non_blocking=True)                                        # :15
-    # F.normalize(..., dim=-1) (:17) through the native library; the bf16 search copy is built
-    # from the same tensor lazily by process_data
+    # F.normalize(..., dim=-1) (:17) through the native library
+    if _dist_info()[2] > 1:
+        from .retrieval import helper_context
+        return helper_context(dev.device).normalize_rows(dev), all_data
+    # single GPU: the bf16 search copy is built from the same tensor right away
     rb = RelatedBank(dev.shape[0], dev.shape[1], device=dev.device)
     bank = rb.normalize_rows(dev)
     rb.upload(bank, 0, normalize=True)
@@ -164,7 +185,8 @@ def _register_bank(bank: torch.Tensor, rb: RelatedBank) -> None:
 
 
 def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnumber: int,
-                 *, exclude_self: bool = False, rescore_fp32: bool = True) -> Iterator[dict]:
+                 *, exclude_self: bool = False, rescore_fp32: bool = True,
+                 dtype: str = "bf16") -> Iterator[dict]:
     """Yield every item with `related_embeddings` = its top-`topnumber` bank rows, best first.
 
     Reference: embeddings_related_generator.py:19-28.  valid_text_embs is the fp32 bank returned
@@ -176,56 +198,137 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
     rescore_fp32 (default on): the fused kernel ranks bf16-rounded operands; its k + 8 best
     candidates are re-scored in fp32 from valid_text_embs, so the k rows kept are the reference's
     fp32 choice also where two captions are closer than the bf16 resolution (~1e-4).
+    dtype="fp32" ranks exact fp32 scores instead (banks up to 65,536 rows, single GPU).
+
+    Batches of queries go through a three-stream pipeline (sharded.SearchPipeline): while the
+    caller pickles the records of batch i, batch i+1 is already being uploaded and searched.
+    Multi-GPU mode (one process per GPU, process group up): the bank is sharded by rows over the
+    ranks, rank r processes — and yields — the contiguous block item_range(len(all_data), r, G);
+    each step all-gathers every rank's query slice, every rank searches (and fp32-re-scores) its
+    shard, an all-to-all returns to each rank the shard lists of its own queries, merged there.
     """
     _require_cuda()
     if not valid_text_embs.is_cuda:
         raise ValueError("valid_text_embs must be the CUDA bank returned by load_data "
                          "(no CPU path exists)")
+    if dtype not in ("bf16", "fp32"):
+        raise ValueError(f"dtype must be 'bf16' or 'fp32', got {dtype!r}")
     topnumber = int(topnumber)
-    rb = bank_for(valid_text_embs, normalize=True)
+    dist, rank, world = _dist_info()
+    if dtype == "fp32":
+        if world > 1:
+            raise ValueError("dtype='fp32' (exact small-bank path) runs on one GPU")
+        yield from _process_exact(valid_text_embs, all_data, topnumber, exclude_self)
+        return
     device = valid_text_embs.device
-    d = valid_text_embs.shape[1]
-    batch: List[dict] = []
-    base = 0
-    # pinned staging buffers, allocated once (page-locking 64 + 335 MB per batch of 16,384 queries
-    # costs more than the search); every flush synchronises the stream before it yields, so the
-    # next flush may overwrite them
-    stage = {}
+    n_bank, d = valid_text_embs.shape
+    from .sharded import SearchPipeline, ShardedRelatedBank
 
-    def pinned(name: str, shape) -> torch.Tensor:
-        buf = stage.get(name)
-        if buf is None or buf.shape[0] < shape[0] or tuple(buf.shape[1:]) != tuple(shape[1:]):
-            # the first batch is the largest one (full batches first, then the ragged tail)
-            buf = torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
-            stage[name] = buf
-        return buf[:shape[0]]
+    if world > 1:
+        all_data = all_data if isinstance(all_data, list) else list(all_data)
+        first, last = item_range(len(all_data), rank, world)
+        per = max(1, min(QUERY_BATCH // world, -(-len(all_data) // world)))
+        n_steps = -(-(-(-len(all_data) // world)) // per)          # same on every rank: collectives inside
+        bank = ShardedRelatedBank(n_bank, d, device=device)
+        bank.upload_global(valid_text_embs, normalize=True)
+        shard_f32 = valid_text_embs[bank.lo:bank.hi]
+        source = iter(all_data[first:last])
+    else:
+        first = 0
+        known = len(all_data) if hasattr(all_data, "__len__") else QUERY_BATCH
+        per = max(1, min(QUERY_BATCH, known))
+        n_steps = None                                             # until the iterable runs dry
+        bank = bank_for(valid_text_embs, normalize=True)
+        shard_f32 = valid_text_embs
+        source = iter(all_data)
+    helper = bank.local if world > 1 else bank
+    pipe = SearchPipeline(bank, world * per, topnumber, depth=2, from_host=True, to_host=False,
+                          result="row_slice", rescore_from=shard_f32 if rescore_fp32 else None,
+                          excludes_self=exclude_self)
+    # pinned staging, allocated once (page-locking costs more than the search); a step's buffers
+    # are free again once its records have been yielded
+    q_stage = [torch.zeros((world * per, d), dtype=torch.float32).pin_memory() for _ in range(2)]
+    r_stage = [torch.empty((per, topnumber, d), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def flush(items: List[dict], first: int) -> Iterator[dict]:
-        q_rows = torch.cat([it["text_embedding"].detach().cpu().reshape(1, -1) for it in items], dim=0)
-        q_host = pinned("queries", q_rows.shape)
-        q_host.copy_(q_rows)                               # casts to fp32 if the records are not
-        q_dev = q_host.to(device, non_blocking=True)
+    def take(n: int) -> List[dict]:
+        out = []
+        for item in source:
+            out.append(item)
+            if len(out) == n:
+                break
+        return out
+
+    def submit(step: int, items: List[dict], base: int):
+        buf = q_stage[step % 2]
+        lo = rank * per
+        if items:
+            rows = torch.cat([it["text_embedding"].detach().cpu().reshape(1, -1) for it in items], dim=0)
+            buf[lo:lo + len(items)].copy_(rows)                   # casts to fp32 if the records are not
+        if len(items) < per:
+            buf[lo + len(items):lo + per].zero_()                  # ragged tail: padding queries, results dropped
         self_index = None
         if exclude_self:
-            self_index = torch.arange(first, first + len(items), dtype=torch.int64, device=device)
-        if rescore_fp32:
-            _, ids = search_rescored(rb, q_dev, valid_text_embs, topnumber, normalize=True,
-                                     self_index=self_index)
-        else:
-            _, ids = rb.search(q_dev, topnumber, normalize_queries=True, self_index=self_index)
-        related = rb.gather_rows(valid_text_embs, ids)                 # [B, k, d] fp32 on the GPU
-        related_host = pinned("related", related.shape)
-        related_host.copy_(related, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+            if world > 1:
+                # global item index of every query row of the all-gathered batch: rank g's slice
+                # holds its items [first_g + step*per, ...)
+                starts = torch.tensor([item_range(len(all_data), g, world)[0] for g in range(world)])
+                self_index = (starts.unsqueeze(1) + step * per + torch.arange(per).unsqueeze(0)).reshape(-1)
+            else:
+                self_index = base + torch.arange(per)
+        return pipe.submit(buf, self_index=self_index)
+
+    step, base = 0, first
+    items = take(per)
+    slot = submit(0, items, base) if (items or world > 1) else None
+    while slot is not None:
+        nxt_items = take(per)
+        more = (step + 1 < n_steps) if n_steps is not None else bool(nxt_items)
+        nxt_slot = submit(step + 1, nxt_items, base + len(items)) if more else None
+        pipe.wait_stream(slot)
+        _, ids = pipe.result_of(slot)                                  # [per, k] global indices, this rank's queries
+        if items:
+            related = helper.gather_rows(valid_text_embs, ids[:len(items)])   # [B, k, d] fp32 on the GPU
+            related_host = r_stage[step % 2][:len(items)]
+            related_host.copy_(related, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            for j, item in enumerate(items):
+                item["text_embedding"] = item["text_embedding"].cpu()      # :25
+                # own storage per record: a view would pickle the whole batch buffer with each item
+                item["related_embeddings"] = related_host[j].clone()       # :26  [k, d] fp32 CPU
+                yield item
+        base += len(items)
+        step, items, slot = step + 1, nxt_items, nxt_slot
+    torch.cuda.synchronize(device)
+    if world > 1:
+        bank.local.close()
+
+
+def _process_exact(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnumber: int,
+                   exclude_self: bool) -> Iterator[dict]:
+    """dtype='fp32': exact fp32 ranking on CUDA cores (zs_exact_topk_f32), small banks only."""
+    from .retrieval import exact_fits, exact_topk, helper_context
+    device = valid_text_embs.device
+    batch_rows = max(1, min(4096, (1 << 28) // max(1, valid_text_embs.shape[0])))
+    if not exact_fits(batch_rows, valid_text_embs.shape[0]):
+        raise ValueError("dtype='fp32' is limited to banks of at most 65,536 rows; use the default "
+                         "bf16 search with fp32 re-scoring")
+    helper = helper_context(device)
+    batch: List[dict] = []
+    base = 0
+
+    def flush(items: List[dict], first: int) -> Iterator[dict]:
+        q = torch.cat([it["text_embedding"].detach().cpu().reshape(1, -1) for it in items], dim=0)
+        self_index = torch.arange(first, first + len(items)) if exclude_self else None
+        _, ids = exact_topk(q.to(device), valid_text_embs, topnumber, normalize=True, self_index=self_index)
+        related_host = helper.gather_rows(valid_text_embs, ids).cpu()
         for j, item in enumerate(items):
-            item["text_embedding"] = item["text_embedding"].cpu()      # :25
-            # own storage per record: a view would pickle the whole batch buffer with each item
-            item["related_embeddings"] = related_host[j].clone()       # :26  [k, d] fp32 CPU
+            item["text_embedding"] = item["text_embedding"].cpu()
+            item["related_embeddings"] = related_host[j].clone()
             yield item
 
     for item in all_data:
         batch.append(item)
-        if len(batch) == QUERY_BATCH:
+        if len(batch) == batch_rows:
             yield from flush(batch, base)
             base += len(batch)
             batch = []
@@ -312,13 +415,38 @@ def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, tota
     once the search takes milliseconds the per-record pickling dominates the script.
     fast_pickle (default: env ZSAAC_FAST_PICKLE=1, else off): pickle tensors through numpy
     (_FastTensorPickler): ~3x faster to write and ~4x faster to read back, same objects after
-    pickle.load, different bytes on disk."""
+    pickle.load, different bytes on disk.
+    Multi-GPU mode: every rank writes the records it processed (process_data yields only those)
+    to `<output_path>.rank<r>`; after a barrier rank 0 appends the rank files, in rank order, to
+    output_path — the same stream one GPU writes — and removes them.  The G ranks pickle in
+    parallel, which is what makes the script scale (pickling, not the search, is the wall clock)."""
     import os
+    import shutil
     if workers is None:
         workers = int(os.environ.get("ZSAAC_WRITER_PROCS", "0"))
     if fast_pickle is None:
         fast_pickle = os.environ.get("ZSAAC_FAST_PICKLE", "0") == "1"
-    with open(output_path, "ab") as file:
+    dist, rank, world = _dist_info()
+    if world > 1:
+        part = f"{output_path}.rank{rank:03d}"
+        first, last = item_range(total_items, rank, world)
+        _write_stream(processed_data_gen, part, "wb", last - first, workers, fast_pickle)
+        dist.barrier()
+        if rank == 0:
+            with open(output_path, "ab") as out:
+                for r in range(world):
+                    piece = f"{output_path}.rank{r:03d}"
+                    with open(piece, "rb") as src:
+                        shutil.copyfileobj(src, out, length=64 << 20)
+                    os.remove(piece)
+        dist.barrier()
+        return
+    _write_stream(processed_data_gen, output_path, "ab", total_items, workers, fast_pickle)
+
+
+def _write_stream(processed_data_gen: Iterable[dict], path: str, mode: str, total_items: int,
+                  workers: int, fast_pickle: bool) -> None:
+    with open(path, mode) as file:
         if workers <= 0:
             for i, item in enumerate(tqdm(processed_data_gen, total=total_items)):
                 _dump_record(item, file, fast_pickle)
@@ -328,10 +456,65 @@ def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, tota
         for item in processed_data_gen:
             batch.append(item)
             if len(batch) == WRITER_BATCH:
-                _write_batch_parallel(batch, file, workers, output_path, fast_pickle)
+                _write_batch_parallel(batch, file, workers, path, fast_pickle)
                 progress.update(len(batch))
                 batch = []
         if batch:
-            _write_batch_parallel(batch, file, workers, output_path, fast_pickle)
+            _write_batch_parallel(batch, file, workers, path, fast_pickle)
             progress.update(len(batch))
         progress.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# CLI shared by the two module mirrors (reference :41-53 / _wavcaps.py:42-54)
+def add_extension_flags(parser) -> None:
+    """Flags the reference does not have (all optional; without them the script behaves like the
+    reference's: one GPU, no self-exclusion, per-record pickles)."""
+    import argparse
+    parser.add_argument('--gpus', type=int, default=1,
+                        help="GPUs of this node to shard the bank over (one process per GPU; the script "
+                             "re-launches itself under torch.distributed.run when it is not already)")
+    parser.add_argument('--exclude_self', action='store_true',
+                        help="do not return item i's own bank row i (the reference keeps it in slot 0)")
+    parser.add_argument('--rescore_fp32', action=argparse.BooleanOptionalAction, default=True,
+                        help="re-score the k + 8 bf16 candidates in fp32 (the reference's precision)")
+    parser.add_argument('--dtype', choices=['bf16', 'fp32'], default='bf16',
+                        help="bf16 tensor-core search (default) or exact fp32 ranking (banks <= 65,536 rows)")
+    # pickle the output records in N forked processes (byte-identical stream)
+    parser.add_argument('--writer_procs', type=int, default=None)
+    # pickle tensors through numpy (same objects after pickle.load, ~3x faster)
+    parser.add_argument('--fast_pickle', action='store_true', default=None)
+
+
+def run_cli(args, module: str, argv, load_fn) -> None:
+    """Body of main() for both mirrors: optional self-launch on N GPUs, then the reference's four
+    lines (load_data -> process_data -> save_data_to_hdf5)."""
+    import os
+    import sys
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world_env == 1:
+        import socket
+        import subprocess
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", module,
+               *(sys.argv[1:] if argv is None else list(argv))]
+        raise SystemExit(subprocess.run(cmd).returncode)
+    if world_env > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    valid_text_embs, all_data = load_fn(args.input_path)
+    processed_data_gen = process_data(valid_text_embs, all_data, args.topnumber,
+                                      exclude_self=args.exclude_self, rescore_fp32=args.rescore_fp32,
+                                      dtype=args.dtype)
+    total_items = len(all_data)
+    save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs,
+                      fast_pickle=args.fast_pickle)
+    if world_env > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()

@@ -177,7 +177,8 @@ class RelatedBank:
         return ranks, scores
 
     def rescore(self, queries: torch.Tensor, bank_f32: torch.Tensor, candidates: torch.Tensor, k: int,
-                *, normalize: bool = True, index_offset: int = 0
+                *, normalize: bool = True, index_offset: int = 0,
+                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Re-score search candidates in fp32 and keep the k best (score desc, index asc).
 
@@ -201,8 +202,15 @@ class RelatedBank:
         if cand.dim() != 2 or cand.shape[0] != q:
             raise ValueError(f"candidates must be [{q}, kc], got {tuple(cand.shape)}")
         kc, k = cand.shape[1], int(k)
-        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
-        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        if out is None:
+            out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        else:
+            out_s, out_i = out
+            if (tuple(out_s.shape) != (q, k) or tuple(out_i.shape) != (q, k)
+                    or out_s.dtype != torch.float32 or out_i.dtype != torch.int64
+                    or not out_s.is_contiguous() or not out_i.is_contiguous()):
+                raise ValueError("out must be contiguous (float32 [Q,k], int64 [Q,k])")
         with torch.cuda.device(self.device):
             _abi.check(self._lib.zs_rescore_f32(
                 self._ctx, queries.data_ptr(), q, 1 if normalize else 0, bank_f32.data_ptr(),
@@ -221,11 +229,14 @@ class RelatedBank:
         return out
 
     # ------------------------------------------------------------------ helpers on the same ctx
-    def merge(self, scores: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def merge(self, scores: torch.Tensor, indices: torch.Tensor,
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
         """k-way merge of [S, Q, k] sorted lists -> [Q, k] under (score desc, index asc).
 
         The S lists may be strided views (dim 0 stride arbitrary, [Q, k] blocks contiguous), e.g.
-        slices of one all-gathered byte buffer."""
+        slices of one all-gathered byte buffer.  `out`: optional preallocated contiguous
+        (float32 [Q, k], int64 [Q, k]) result tensors."""
         if scores.dim() != 3 or scores.shape != indices.shape:
             raise ValueError("merge expects scores and indices of identical shape [S, Q, k]")
         s, q, k = scores.shape
@@ -239,8 +250,15 @@ class RelatedBank:
             scores = scores.contiguous()
         if not blocks_contiguous(indices):
             indices = indices.contiguous()
-        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
-        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        if out is None:
+            out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        else:
+            out_s, out_i = out
+            if (tuple(out_s.shape) != (q, k) or tuple(out_i.shape) != (q, k)
+                    or out_s.dtype != torch.float32 or out_i.dtype != torch.int64
+                    or not out_s.is_contiguous() or not out_i.is_contiguous()):
+                raise ValueError("out must be contiguous (float32 [Q,k], int64 [Q,k])")
         s_stride = scores.stride(0) if s > 1 else q * k
         i_stride = indices.stride(0) if s > 1 else q * k
         with torch.cuda.device(self.device):

@@ -148,3 +148,195 @@ class ShardedRelatedBank:
         all_scores = gathered[:, :q * k * 4].view(torch.float32).view(self.world, q, k)
         all_index = gathered[:, score_bytes:].view(torch.int64).view(self.world, q, k)
         return self.local.merge(all_scores, all_index)
+
+
+class SearchPipeline:
+    """Software pipeline of searches against one (sharded) bank: three CUDA streams per rank.
+
+        input   : this rank's slice of the host query batch -> device (pinned H2D) and the
+                  all-gather that replicates the batch over NVLink            [batch i+1]
+        search  : normalise + cast -> fused similarity / top-k over the shard  [batch i]
+        output  : exchange of the shard-local lists, k-way merge, D2H          [batch i-1]
+
+    Every search of a sharded bank ends in an exchange + merge (and, end to end, begins with an
+    upload); issued on one stream those serialise with the fused kernel (1.6 ms of a 111 ms step
+    at 8 GPUs in round 1, 5 ms more end to end).  Here they run on side streams with `depth`
+    buffer sets, two extra NCCL communicators keep the input and output collectives independent
+    of each other, and the fused kernels of consecutive batches run back to back.
+
+    result="replicated": all-gather + merge of all Q rows on every rank (what
+    ShardedRelatedBank.search returns).  result="row_slice": rank r ends up with the global top-k
+    of query rows [r*ceil(Q/G), (r+1)*ceil(Q/G)) only — an all-to-all moves 1/G of the lists to
+    each rank, which merges (and copies out) 1/G of the rows: the natural form when each process
+    hands its share of the result to the host.
+
+    rescore_from: the fp32 rows of THIS rank's shard ([local rows, d], unit rows or raw — cosine
+    is recomputed).  The search stage then fetches k + rescore_margin bf16 candidates from the
+    shard, re-scores them in fp32 (zs_rescore_f32) and passes its k best ON: shard lists carry
+    fp32 scores, so the merged result is the fp32 ranking (reference
+    embeddings_related_generator.py:22) wherever the true top-k lies inside the candidate sets.
+    """
+
+    def __init__(self, bank, n_queries: int, k: int, *, depth: int = 2, from_host: bool = True,
+                 to_host: bool = True, result: str = "replicated",
+                 self_index: Optional[torch.Tensor] = None, normalize_queries: bool = True,
+                 query_dtype: torch.dtype = torch.float32,
+                 rescore_from: Optional[torch.Tensor] = None, rescore_margin: int = 8,
+                 excludes_self: bool = False):
+        if result not in ("replicated", "row_slice"):
+            raise ValueError(f"result must be 'replicated' or 'row_slice', got {result!r}")
+        self.sharded = isinstance(bank, ShardedRelatedBank)
+        self.bank = bank
+        self.local = bank.local if self.sharded else bank
+        self.world = bank.world if self.sharded else 1
+        self.rank = bank.rank if self.sharded else 0
+        self.group = bank.group if self.sharded else None
+        self.device = self.local.device
+        self.q, self.k, self.dim = int(n_queries), int(k), self.local.dim
+        self.from_host, self.to_host, self.result = from_host, to_host, result
+        self.self_index = self_index
+        self.normalize_queries = normalize_queries
+        self.rescore_from = rescore_from
+        self.kc = self.k
+        if rescore_from is not None:
+            if rescore_from.dtype != torch.float32 or rescore_from.shape[0] != self.local.rows:
+                raise ValueError("rescore_from must be the float32 rows of this rank's shard")
+            if not from_host and query_dtype != torch.float32:
+                raise TypeError("fp32 re-scoring needs float32 queries")
+            avail = self.local.rows - (1 if (self_index is not None or excludes_self) else 0)
+            from . import _abi
+            self.kc = max(self.k, min(self.k + int(rescore_margin), _abi.ZS_MAX_K, avail))
+        G, q, dev = self.world, self.q, self.device
+        self.per = -(-q // G)                          # query rows per rank (input slices, row_slice results)
+        self.lo = min(self.rank * self.per, q)
+        self.hi = min(self.lo + self.per, q)
+        self.g_in = self.g_out = None
+        if G > 1:
+            ranks = list(range(dist.get_world_size(self.group)))
+            if self.group is not None:
+                ranks = dist.get_process_group_ranks(self.group)
+            self.g_in = dist.new_group(ranks)          # own communicators: the three stages' collectives
+            self.g_out = dist.new_group(ranks)         # must not queue behind one another
+        self.s_in, self.s_main, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        rows_out = self.per if (result == "row_slice" and G > 1) else q
+        self.rows_out = rows_out
+        self.slots = []
+        for _ in range(depth):
+            slot = {
+                "q_full": torch.empty((G * self.per, self.dim), dtype=query_dtype, device=dev) if from_host else None,
+                "local_s": torch.empty((G * self.per, self.k), dtype=torch.float32, device=dev),
+                "local_i": torch.empty((G * self.per, self.k), dtype=torch.int64, device=dev),
+                "out_s": torch.empty((rows_out, self.k), dtype=torch.float32, device=dev),
+                "out_i": torch.empty((rows_out, self.k), dtype=torch.int64, device=dev),
+                "in_done": torch.cuda.Event(), "search_done": torch.cuda.Event(),
+                "out_done": torch.cuda.Event(), "used": False,
+            }
+            if rescore_from is not None:
+                slot["cand_s"] = torch.empty((self.q, self.kc), dtype=torch.float32, device=dev)
+                slot["cand_i"] = torch.empty((self.q, self.kc), dtype=torch.int64, device=dev)
+            if G > 1:
+                slot["recv_s"] = torch.empty((G, rows_out, self.k), dtype=torch.float32, device=dev)
+                slot["recv_i"] = torch.empty((G, rows_out, self.k), dtype=torch.int64, device=dev)
+            if to_host:
+                slot["host_s"] = torch.empty((rows_out, self.k), dtype=torch.float32).pin_memory()
+                slot["host_i"] = torch.empty((rows_out, self.k), dtype=torch.int64).pin_memory()
+            self.slots.append(slot)
+        self.local.reserve(self.q, self.kc)
+        self._next = 0
+        self.h2d_bytes = (self.hi - self.lo) * self.dim * torch.empty((), dtype=query_dtype).element_size() if from_host else 0
+        self.d2h_bytes = rows_out * self.k * 12 if to_host else 0
+
+    @property
+    def out_rows(self) -> Tuple[int, int]:
+        """[lo, hi) query rows whose global top-k this rank's outputs hold."""
+        if self.result == "row_slice" and self.world > 1:
+            return self.lo, self.hi
+        return 0, self.q
+
+    def submit(self, queries: torch.Tensor, *, self_index: Optional[torch.Tensor] = None) -> int:
+        """Enqueue one batch ([Q, d]: pinned host tensor if from_host — only rows [lo, hi) of this
+        rank are read — else a device tensor that must stay untouched until the slot is waited
+        for).  self_index overrides the pipeline's for this batch.  Returns the slot holding the
+        result."""
+        if self_index is None:
+            self_index = self.self_index
+        if self_index is not None:
+            self_index = self_index.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        idx = self._next
+        self._next = (self._next + 1) % len(self.slots)
+        slot = self.slots[idx]
+        cur = torch.cuda.current_stream(self.device)
+        G = self.world
+        if self.from_host:
+            with torch.cuda.stream(self.s_in):
+                if slot["used"]:
+                    self.s_in.wait_event(slot["search_done"])      # the previous search read q_full
+                else:
+                    self.s_in.wait_stream(cur)
+                q_full = slot["q_full"]
+                mine = q_full[self.rank * self.per:(self.rank + 1) * self.per]
+                if self.hi > self.lo:
+                    mine[:self.hi - self.lo].copy_(queries[self.lo:self.hi], non_blocking=True)
+                if G > 1:
+                    dist.all_gather_into_tensor(q_full.view(-1), mine.reshape(-1), group=self.g_in)
+                slot["in_done"].record(self.s_in)
+            q_dev = q_full[:self.q]
+        else:
+            q_dev = queries
+        with torch.cuda.stream(self.s_main):
+            if self.from_host:
+                self.s_main.wait_event(slot["in_done"])
+            elif not slot["used"]:
+                self.s_main.wait_stream(cur)
+            if slot["used"]:
+                self.s_main.wait_event(slot["out_done"])          # local_s / local_i are free again
+            if self.rescore_from is None:
+                self.local.search(q_dev, self.k, normalize_queries=self.normalize_queries,
+                                  self_index=self_index,
+                                  out=(slot["local_s"][:self.q], slot["local_i"][:self.q]))
+            else:
+                self.local.search(q_dev, self.kc, normalize_queries=self.normalize_queries,
+                                  self_index=self_index, out=(slot["cand_s"], slot["cand_i"]))
+                self.local.rescore(q_dev, self.rescore_from, slot["cand_i"], self.k,
+                                   normalize=self.normalize_queries, index_offset=self.local.index_offset,
+                                   out=(slot["local_s"][:self.q], slot["local_i"][:self.q]))
+            slot["search_done"].record(self.s_main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["search_done"])
+            if G == 1:
+                res_s, res_i = slot["local_s"][:self.q], slot["local_i"][:self.q]
+            else:
+                if self.result == "row_slice":
+                    dist.all_to_all_single(slot["recv_s"].view(-1), slot["local_s"].view(-1), group=self.g_out)
+                    dist.all_to_all_single(slot["recv_i"].view(-1), slot["local_i"].view(-1), group=self.g_out)
+                else:
+                    dist.all_gather_into_tensor(slot["recv_s"].view(-1), slot["local_s"][:self.q].reshape(-1), group=self.g_out)
+                    dist.all_gather_into_tensor(slot["recv_i"].view(-1), slot["local_i"][:self.q].reshape(-1), group=self.g_out)
+                self.local.merge(slot["recv_s"], slot["recv_i"], out=(slot["out_s"], slot["out_i"]))
+                res_s, res_i = slot["out_s"], slot["out_i"]
+            if self.to_host:
+                slot["host_s"].copy_(res_s, non_blocking=True)
+                slot["host_i"].copy_(res_i, non_blocking=True)
+            slot["out_done"].record(self.s_out)
+            slot["res"] = (res_s, res_i)
+        slot["keepalive"] = (queries, self_index)     # inputs of kernels still queued on the side streams
+        slot["used"] = True
+        return idx
+
+    def wait_stream(self, idx: Optional[int] = None) -> None:
+        """Make the current stream wait for slot `idx` (all slots if None) — no host sync."""
+        cur = torch.cuda.current_stream(self.device)
+        for j, slot in enumerate(self.slots):
+            if slot["used"] and (idx is None or idx == j):
+                cur.wait_event(slot["out_done"])
+
+    def result_of(self, idx: int, *, host: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Result tensors of slot `idx` (device, or the pinned host copies); the caller must have
+        waited (wait_stream, or a host synchronise for the host copies).  Rows out_rows."""
+        slot = self.slots[idx]
+        if host:
+            n = self.out_rows[1] - self.out_rows[0]
+            return slot["host_s"][:n], slot["host_i"][:n]
+        s, i = slot["res"]
+        n = self.out_rows[1] - self.out_rows[0]
+        return s[:n], i[:n]
