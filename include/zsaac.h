@@ -222,11 +222,14 @@ int zs_profile_read(zs_ctx* ctx, float* ms_out, int max_entries, int* n_entries)
 int zs_debug_scores(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype,
                     int normalize_queries, float* out_scores, void* stream);
 
-/* Test / tuning hook: while `stamps` is non-NULL every CTA of the fused kernel writes 8 uint64
- * %globaltimer values (ns) to stamps[cta*8 + i]: 0 entry, 1 barriers+TMEM ready, 2 first bank
- * tile's MMAs complete, 3 last tile of the last unit scanned, 4 lists written, 5 exit; 6 / 7 are clock64() at entry /
- * exit (SM cycles, so (7-6)/(5-0) is the SM clock in GHz during the kernel).  The
- * device buffer [n_ctas, 8] is caller-owned; pass NULL to switch tracing off. */
+/* Test / tuning hook: while `stamps` is non-NULL every CTA of the fused kernel writes uint64
+ * %globaltimer values (ns) to stamps[cta*16 + i]: 0 entry, 1 barriers+TMEM ready, 2 first bank
+ * tile's MMAs complete, 3 last tile of the last unit scanned, 4 lists written, 5 exit (after the
+ * in-kernel merge in single-launch mode); 6 / 7 are clock64() at entry / exit (SM cycles, so
+ * (7-6)/(5-0) is the SM clock in GHz during the kernel); single-launch mode only: 8 this CTA's
+ * query rows cast, 9 all queries cast (first load may start), 10 all CTAs' lists written (merge
+ * starts); 11-15 unused.  The device buffer [n_ctas, 16] is caller-owned; pass NULL to switch
+ * tracing off. */
 int zs_debug_trace(zs_ctx* ctx, void* stamps);
 
 /* Name of the dominant kernel (for ncu -k) and ABI version. */

@@ -9,10 +9,8 @@ import zsaac_b200
 
 dev = torch.device("cuda", 0)
 CASES = [  # Q, N, k, cta_group, forced chunks (0 = planner)
-    (975, 49838, 10, "1", 0), (975, 49838, 10, "2", 0), (975, 49838, 1, "2", 0),
-    (975, 49838, 10, "2", 9), (975, 49838, 10, "1", 9), (975, 49838, 10, "1", 4),
-    (1045, 19195, 5, "2", 0), (128, 400000, 10, "1", 0), (8192, 400000, 10, "2", 0),
-    (16384, 400000, 32, "2", 0), (16384, 400000, 10, "2", 0),
+    (975, 49838, 10, "2", 0), (975, 49838, 1, "2", 0), (1045, 19195, 5, "1", 0), (1045, 19195, 5, "2", 0),
+    (256, 400000, 10, "2", 0), (128, 400000, 10, "1", 0), (8192, 400000, 10, "2", 0),
 ]
 for (Q, N, k, cg, chunks_forced) in CASES:
     os.environ["ZSAAC_CTA_GROUP"] = cg
@@ -27,7 +25,7 @@ for (Q, N, k, cg, chunks_forced) in CASES:
     chunks, tpc, ctas = rb.plan(Q, k)
     for _ in range(20):                       # keep the GPU busy so the clocks are up
         rb.search(q, k)
-    stamps = torch.zeros(ctas, 8, dtype=torch.int64, device=dev)
+    stamps = torch.zeros(ctas, 16, dtype=torch.int64, device=dev)
     rb.trace(stamps)
     rb.profile(True)
     rb.search(q, k)
@@ -36,7 +34,7 @@ for (Q, N, k, cg, chunks_forced) in CASES:
     rb.trace(None)
     t = stamps.cpu().double()
     t0 = t[:, 0].min()
-    rel = (t[:, :6] - t0) / 1e3            # us
+    rel = (t[:, :11] - t0) / 1e3            # us
     names = ["entry", "setup done", "1st tile MMA done", "last tile scanned", "lists written", "exit"]
     ghz = ((t[:, 7] - t[:, 6]) / (t[:, 5] - t[:, 0])).median()
     units_per_cta = -(-(chunks * -(-Q // (128 * int(cg)))) // (ctas // int(cg)))
@@ -45,6 +43,10 @@ for (Q, N, k, cg, chunks_forced) in CASES:
     for i, n in enumerate(names):
         col = rel[:, i]
         print(f"  {n:20s} min {col.min():8.2f}  median {col.median():8.2f}  max {col.max():8.2f} us")
+    if t[:, 8].max() > 0:                  # single-launch mode
+        for i, n in ((8, "own rows cast"), (9, "all rows cast"), (10, "all lists written")):
+            col = rel[:, i][t[:, i] > 0]
+            print(f"  {n:20s} min {col.min():8.2f}  median {col.median():8.2f}  max {col.max():8.2f} us")
     busy = (rel[:, 3] - rel[:, 2]).median()
     tiles = units_per_cta * tpc
     per_tile = busy / max(tiles - 1, 1)

@@ -24,23 +24,71 @@ __device__ __forceinline__ float warp_sum(float v) {
 // 8-byte/16-byte vectors.
 // The sum of squares is accumulated in a fixed order (lane-strided, then xor butterfly), so the
 // result does not depend on the launch geometry (nor on which kernel calls this).
+template <typename InT>
+__device__ __forceinline__ void load4(const InT* __restrict__ p, float& x0, float& x1, float& x2, float& x3) {
+  if constexpr (sizeof(InT) == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+  } else {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
+  }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* __restrict__ p, float y0, float y1, float y2, float y3) {
+  if constexpr (sizeof(OutT) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(y0, y1, y2, y3);
+  } else {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(y2, y3);
+    uint2 packed;
+    packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+    packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = packed;
+  }
+}
+
+// Rows up to 1024 elements (the path's d) are held in registers between the sum of squares and
+// the scaling, so the row is read once and all its loads are in flight together (one memory
+// round trip instead of two); longer rows take two passes.  Same summation order either way.
 template <typename InT, typename OutT>
 __device__ __forceinline__ void normalize_cast_row(const InT* __restrict__ src, OutT* __restrict__ dst,
                                                    int d, int normalize, int lane) {
-  float denom = 1.0f;   // F.normalize divides by max(||x||, eps); x / 1 is exact when not normalising
+  if (d <= 1024) {
+    float x[8][4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int c = lane * 4 + t * 128;
+      if (c < d) load4(src + c, x[t][0], x[t][1], x[t][2], x[t][3]);
+      else x[t][0] = x[t][1] = x[t][2] = x[t][3] = 0.0f;
+    }
+    float denom = 1.0f;   // F.normalize divides by max(||x||, eps); x / 1 is exact when not normalising
+    if (normalize) {
+      float ss = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        ss = fmaf(x[t][0], x[t][0], ss); ss = fmaf(x[t][1], x[t][1], ss);
+        ss = fmaf(x[t][2], x[t][2], ss); ss = fmaf(x[t][3], x[t][3], ss);
+      }
+      ss = warp_sum(ss);
+      denom = fmaxf(sqrtf(ss), 1e-12f);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int c = lane * 4 + t * 128;
+      if (c < d) store4(dst + c, x[t][0] / denom, x[t][1] / denom, x[t][2] / denom, x[t][3] / denom);
+    }
+    return;
+  }
+  float denom = 1.0f;
   if (normalize) {
     float ss = 0.0f;
     for (int c = lane * 4; c < d; c += 128) {
       float x0, x1, x2, x3;
-      if constexpr (sizeof(InT) == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + c);
-        x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
-      } else {
-        const uint2 raw = *reinterpret_cast<const uint2*>(src + c);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
-      }
+      load4(src + c, x0, x1, x2, x3);
       ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
     }
     ss = warp_sum(ss);
@@ -48,25 +96,8 @@ __device__ __forceinline__ void normalize_cast_row(const InT* __restrict__ src, 
   }
   for (int c = lane * 4; c < d; c += 128) {
     float x0, x1, x2, x3;
-    if constexpr (sizeof(InT) == 4) {
-      const float4 v = *reinterpret_cast<const float4*>(src + c);
-      x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
-    } else {
-      const uint2 raw = *reinterpret_cast<const uint2*>(src + c);
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-      x0 = __low2float(a); x1 = __high2float(a); x2 = __low2float(b); x3 = __high2float(b);
-    }
-    if constexpr (sizeof(OutT) == 4) {
-      *reinterpret_cast<float4*>(dst + c) = make_float4(x0 / denom, x1 / denom, x2 / denom, x3 / denom);
-    } else {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 / denom, x1 / denom);
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 / denom, x3 / denom);
-      uint2 packed;
-      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
-      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dst + c) = packed;
-    }
+    load4(src + c, x0, x1, x2, x3);
+    store4(dst + c, x0 / denom, x1 / denom, x2 / denom, x3 / denom);
   }
 }
 
@@ -174,6 +205,65 @@ __device__ __forceinline__ void warp_merge(int n_lists, int k, int lane, Load lo
   }
 }
 
+// The same merge on PACKED keys, for lists whose indices fit 32 bits (the chunk partials of the
+// fused kernel: columns within a shard).  key = (order-preserving score bits << 32) | ~column, so
+// "better under (score desc, column asc)" is one unsigned 64-bit compare and a pick is a 64-bit
+// max: ~30 dependent instructions per round instead of ~120 — what counts when ONE warp merges
+// one query's lists while nothing else is left to run (small searches, single-launch mode).
+// Exhausted lists present key 0; empty slots (-inf, IDX 0x7fffffff) present a small non-zero key.
+__device__ __forceinline__ unsigned long long pack_key(float s, int col) {
+  unsigned int u = __float_as_uint(s);
+  if (u == 0x80000000u) u = 0u;                 // -0 == +0 in the float order the lists were built with
+  const unsigned int sk = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<unsigned long long>(sk) << 32) | (0xffffffffu - static_cast<unsigned int>(col));
+}
+__device__ __forceinline__ void unpack_key(unsigned long long key, float& s, long long& col) {
+  const unsigned int sk = static_cast<unsigned int>(key >> 32);
+  s = __uint_as_float((sk & 0x80000000u) ? (sk & 0x7fffffffu) : ~sk);
+  const unsigned int c = 0xffffffffu - static_cast<unsigned int>(key);
+  col = (c == 0x7fffffffu) ? 0x7fffffffffffffffll : static_cast<long long>(c);
+}
+
+// load_key(list, pos) -> packed key; store(r, score, column-or-SENT)
+template <int LPL, typename LoadKey, typename Store>
+__device__ __forceinline__ void warp_merge_keys(int n_lists, int k, int lane, LoadKey load_key, Store store) {
+  int head[LPL];
+  unsigned long long hk[LPL], nk[LPL];
+#pragma unroll
+  for (int l = 0; l < LPL; ++l) {
+    const int list = lane + 32 * l;
+    head[l] = 0;
+    hk[l] = nk[l] = 0ull;
+    if (list < n_lists) {
+      hk[l] = load_key(list, 0);
+      if (k > 1) nk[l] = load_key(list, 1);
+    } else {
+      head[l] = k;
+    }
+  }
+  for (int r = 0; r < k; ++r) {
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int l = 0; l < LPL; ++l) best = max(best, hk[l]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+      float s = -CUDART_INF_F;
+      long long col = 0x7fffffffffffffffll;
+      if (best != 0ull) unpack_key(best, s, col);
+      store(r, s, col);
+    }
+#pragma unroll
+    for (int l = 0; l < LPL; ++l) {
+      if (best != 0ull && hk[l] == best) {       // the owner(s) of the pick advance
+        ++head[l];
+        hk[l] = (head[l] < k) ? nk[l] : 0ull;
+        nk[l] = (head[l] + 1 < k) ? load_key(lane + 32 * l, head[l] + 1) : 0ull;
+      }
+    }
+  }
+}
+
 // One warp per query: enough parallelism whenever there are many queries.
 template <typename IdxT, int LPL>
 __global__ void __launch_bounds__(256)
@@ -185,16 +275,27 @@ merge_lists_kernel(const float* __restrict__ scores, const IdxT* __restrict__ id
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;
   const long long SENT = 0x7fffffffffffffffll;
-  warp_merge<LPL>(
-      S, k, lane,
-      [&](int list, int pos, float& s, long long& i) {
-        s = scores[static_cast<int64_t>(list) * score_stride + q * k + pos];
-        i = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k + pos]);
-      },
-      [&](int r, float s, long long i) {
-        out_scores[q * out_stride + r] = s;
-        out_idx[q * out_stride + r] = (i == SENT) ? -1ll : i + idx_offset;
-      });
+  auto store = [&](int r, float s, long long i) {
+    out_scores[q * out_stride + r] = s;
+    out_idx[q * out_stride + r] = (i == SENT) ? -1ll : i + idx_offset;
+  };
+  if constexpr (sizeof(IdxT) == 4) {
+    warp_merge_keys<LPL>(
+        S, k, lane,
+        [&](int list, int pos) {
+          return pack_key(scores[static_cast<int64_t>(list) * score_stride + q * k + pos],
+                          static_cast<int>(idx[static_cast<int64_t>(list) * index_stride + q * k + pos]));
+        },
+        store);
+  } else {
+    warp_merge<LPL>(
+        S, k, lane,
+        [&](int list, int pos, float& s, long long& i) {
+          s = scores[static_cast<int64_t>(list) * score_stride + q * k + pos];
+          i = widen_index(idx[static_cast<int64_t>(list) * index_stride + q * k + pos]);
+        },
+        store);
+  }
 }
 
 // One block per query, for few queries with many lists (a small batch against a bank split into
@@ -219,16 +320,25 @@ merge_lists_block_kernel(const float* __restrict__ scores, const IdxT* __restric
   const int per_warp = (S + MERGE_BLOCK_WARPS - 1) / MERGE_BLOCK_WARPS;   // <= 64: two lists per lane
   const int first = warp * per_warp;
   const int mine = max(0, min(per_warp, S - first));
-  warp_merge<2>(
-      mine, k, lane,
-      [&](int list, int pos, float& s, long long& i) {
-        s = scores[static_cast<int64_t>(first + list) * score_stride + q * k + pos];
-        i = widen_index(idx[static_cast<int64_t>(first + list) * index_stride + q * k + pos]);
-      },
-      [&](int r, float s, long long i) {
-        part_s[warp][r] = s;
-        part_i[warp][r] = i;
-      });
+  auto load_mine = [&](int list, int pos, float& s, long long& i) {
+    s = scores[static_cast<int64_t>(first + list) * score_stride + q * k + pos];
+    i = widen_index(idx[static_cast<int64_t>(first + list) * index_stride + q * k + pos]);
+  };
+  auto store_part = [&](int r, float s, long long i) {
+    part_s[warp][r] = s;
+    part_i[warp][r] = i;
+  };
+  if constexpr (sizeof(IdxT) == 4) {
+    warp_merge_keys<2>(
+        mine, k, lane,
+        [&](int list, int pos) {
+          return pack_key(scores[static_cast<int64_t>(first + list) * score_stride + q * k + pos],
+                          static_cast<int>(idx[static_cast<int64_t>(first + list) * index_stride + q * k + pos]));
+        },
+        store_part);
+  } else {
+    warp_merge<2>(mine, k, lane, load_mine, store_part);
+  }
   __syncthreads();
   if (warp == 0) {
     warp_merge<1>(

@@ -86,7 +86,7 @@ struct SimTopkParams {
   int n_targets;
   int* part_counts;          // [num_chunks * EPI_HALVES, Q, n_targets]
   int* err_flag;
-  unsigned long long* trace;  // nullable: [gridDim.x, 8] globaltimer stamps (zs_debug_trace)
+  unsigned long long* trace;  // nullable: [gridDim.x, 16] globaltimer stamps (zs_debug_trace)
   // Soft lock-step of the bank stream (nullable = off).  All workers walk units of identical
   // length in the same order, so "window w" (sync_window consecutive bank tiles of a unit
   // iteration) covers the same tile positions for everyone.  A worker starts loading window w
@@ -189,11 +189,12 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+constexpr int TRACE_SLOTS = 16;
 __device__ __forceinline__ void trace_stamp(const SimTopkParams& p, int slot) {
   if (p.trace != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.trace[static_cast<size_t>(blockIdx.x) * 8 + slot] = t;
+    p.trace[static_cast<size_t>(blockIdx.x) * TRACE_SLOTS + slot] = t;
   }
 }
 
@@ -355,42 +356,28 @@ __device__ __forceinline__ void grid_wait(const unsigned long long* cnt, unsigne
       : "memory");
 }
 
-template <int LPL>
-__device__ __forceinline__ void solo_merge_row(const float* part_scores, const int* part_idx,
-                                               int n_lists, size_t list_stride, int row, int k,
-                                               long long index_offset, float* out_scores,
-                                               long long* out_idx, long long out_stride, int lane) {
-  const long long SENT = 0x7fffffffffffffffll;
-  // the lists were written by other CTAs of this same launch: read them through L2 (.cg), never
-  // through the non-coherent path
-  warp_merge<LPL>(
-      n_lists, k, lane,
-      [&](int list, int pos, float& sc, long long& ix) {
-        const size_t o = static_cast<size_t>(list) * list_stride + static_cast<size_t>(row) * k + pos;
-        sc = __ldcg(part_scores + o);
-        ix = widen_index(__ldcg(part_idx + o));
-      },
-      [&](int r, float sc, long long ix) {
-        out_scores[static_cast<size_t>(row) * out_stride + r] = sc;
-        out_idx[static_cast<size_t>(row) * out_stride + r] = (ix == SENT) ? -1ll : ix + index_offset;
-      });
-}
-
-// Rows are dealt round-robin to all warps of the grid.
+// Rows are dealt round-robin to all warps of the grid.  One-shot code: kept small on purpose — a
+// larger variant that staged the keys in shared memory first was SLOWER (profiles/r02/SUMMARY.md:
+// this phase is dominated by fetching cold instructions, not by its loads).
 __device__ __noinline__ void solo_merge(const float* part_scores, const int* part_idx, int n_lists,
                                         int Q, int k, long long index_offset, float* out_scores,
                                         long long* out_idx, long long out_stride, int gwarp,
                                         int n_gwarps, int lane) {
   const size_t list_stride = static_cast<size_t>(Q) * k;
+  const long long SENT = 0x7fffffffffffffffll;
   for (int row = gwarp; row < Q; row += n_gwarps) {
-    if (n_lists <= 32)
-      solo_merge_row<1>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
-    else if (n_lists <= 64)
-      solo_merge_row<2>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
-    else if (n_lists <= 256)
-      solo_merge_row<8>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
-    else
-      solo_merge_row<16>(part_scores, part_idx, n_lists, list_stride, row, k, index_offset, out_scores, out_idx, out_stride, lane);
+    // the lists were written by other CTAs of this same launch: read them through L2 (.cg),
+    // never through the non-coherent path
+    auto load_key = [&](int list, int pos) {
+      const size_t o = static_cast<size_t>(list) * list_stride + static_cast<size_t>(row) * k + pos;
+      return pack_key(__ldcg(part_scores + o), __ldcg(part_idx + o));
+    };
+    auto store = [&](int r, float sc, long long ix) {
+      out_scores[static_cast<size_t>(row) * out_stride + r] = sc;
+      out_idx[static_cast<size_t>(row) * out_stride + r] = (ix == SENT) ? -1ll : ix + index_offset;
+    };
+    if (n_lists <= 64) warp_merge_keys<2>(n_lists, k, lane, load_key, store);
+    else warp_merge_keys<16>(n_lists, k, lane, load_key, store);
   }
 }
 
@@ -433,7 +420,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (threadIdx.x == 0) {
     trace_stamp(p, 0);                                   // kernel entry
-    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + 6] = clock64();
+    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * TRACE_SLOTS + 6] = clock64();
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
@@ -465,7 +452,34 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // Solo mode, distributed prologue: the warps of the whole grid share the rows of the query
   // batch (F.normalize + bf16 cast into the workspace the query tensor map points at); the TMA
   // producers wait for the grid-wide arrival counter before their first query load.
+  // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
+  uint32_t full_leader0 = full_bar(0);
+  if constexpr (CG == 2) {
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
+    full_leader0 = __shfl_sync(0xffffffffu, full_leader0, 0);
+  }
+  int pre_issued = 0;     // producer: ring slots whose bank half is already in flight
   if (MODE == MODE_TOPK && p.solo != 0 && p.q_src != nullptr) {
+    // The bank does not depend on the cast: the producer puts the bank half of its first ring
+    // slots in flight now (each slot's barrier is armed for the full slot, so the MMA still waits
+    // for the query half) and the cold HBM latency of the first loads hides behind the cast.
+    if (warp == 0 && worker < num_units) {
+      const int b_row = (worker / p.num_m_tiles) * p.tiles_per_chunk * BLOCK_N +
+                        static_cast<int>(cta_rank) * (BLOCK_N / CG);
+      pre_issued = min(STAGES, p.num_k_blocks);
+      for (int st = 0; st < pre_issued; ++st) {
+        const uint32_t b_dst = base_u32 + st * STAGE_STRIDE + A_STAGE_BYTES;
+        if (ptx::elect_one()) {
+          if constexpr (CG == 1) {
+            ptx::mbar_arrive_expect_tx(full_bar(st), TX_BYTES);
+            ptx::tma_load_2d(b_dst, &tmap_b, full_bar(st), st * BLOCK_K, b_row);
+          } else {
+            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(st), TX_BYTES);
+            ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader0 + 8u * st, st * BLOCK_K, b_row);
+          }
+        }
+      }
+    }
     const int n_gwarps = static_cast<int>(gridDim.x) * (NUM_THREADS / 32);
     for (int r = static_cast<int>(blockIdx.x) * (NUM_THREADS / 32) + warp; r < p.q_pad; r += n_gwarps) {
       __nv_bfloat16* dst = p.q_ws + static_cast<size_t>(r) * p.d;
@@ -479,12 +493,14 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                            p.d, p.q_normalize, lane);
       }
     }
-    // generic-proxy writes, read by other CTAs' TMA (async proxy): proxy fence + gpu-scope fence
-    // on the writer side, counter acquire + proxy fence on the reader side
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __threadfence();
+    // generic-proxy writes, read by other CTAs' TMA (async proxy): CTA barrier + one cumulative
+    // gpu-scope fence on the writer side, counter acquire + proxy fence on the reader side
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(p.grid_cnt, 1ull);
+    if (threadIdx.x == 0) {
+      __threadfence();          // cumulative: orders the whole CTA's row writes (seen through the barrier)
+      atomicAdd(p.grid_cnt, 1ull);
+      trace_stamp(p, 8);                                   // this CTA's share of the queries is cast
+    }
   }
 
   // The producer and the MMA issuer run their loops with the WHOLE warp (all values warp-uniform)
@@ -497,18 +513,14 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    // pair: operand bytes of both CTAs are accounted on the LEADER's full barrier
-    uint32_t full_leader0 = full_bar(0);
-    if constexpr (CG == 2) {
-      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full_bar(0)));
-      full_leader0 = __shfl_sync(0xffffffffu, full_leader0, 0);
-    }
+    int issued = 0;
     const bool sync_on = (p.sync_cnt != nullptr) && is_leader;   // the leader paces the pair
     bool sync_wait = sync_on;
     int iter = 0;
     if (MODE == MODE_TOPK && p.solo != 0 && p.q_src != nullptr) {
       grid_wait(p.grid_cnt, p.cast_target, p.err_flag, ERR_GRID_CAST);   // every CTA has cast its rows
       asm volatile("fence.proxy.async;" ::: "memory");
+      if (lane == 0) trace_stamp(p, 9);                    // the whole batch is cast: loads may start
     }
     for (int u = worker; u < num_units; u += num_workers, ++iter) {
       const int m_tile = u % p.num_m_tiles;
@@ -537,19 +549,21 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
           //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
           //  only look-ahead)
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
+          const bool bank_in_flight = issued < pre_issued;   // armed + bank half loaded in the prologue
+          ++issued;
+          if (!bank_in_flight) ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);
           const uint32_t a_dst = base_u32 + stage * STAGE_STRIDE;
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           if (ptx::elect_one()) {
             if constexpr (CG == 1) {
-              ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              if (!bank_in_flight) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
               ptx::tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BLOCK_K, q_row);
-              ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+              if (!bank_in_flight) ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
             } else {
-              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
+              if (is_leader && !bank_in_flight) ptx::mbar_arrive_expect_tx(full_bar(stage), TX_BYTES);
               const uint32_t full_leader = full_leader0 + 8u * stage;
               ptx::tma_load_2d_cg2(a_dst, &tmap_q, full_leader, kb * BLOCK_K, q_row);
-              ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+              if (!bank_in_flight) ptx::tma_load_2d_cg2(b_dst, &tmap_b, full_leader, kb * BLOCK_K, b_row);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -815,6 +829,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         atomicAdd(p.grid_cnt + 1, 1ull);
       }
       grid_wait(p.grid_cnt + 1, p.done_target, p.err_flag, ERR_GRID_DONE);
+      if (threadIdx.x == 0) trace_stamp(p, 10);            // every CTA's lists are written
       solo_merge(p.part_scores, p.part_idx, p.num_chunks * EPI_HALVES, p.Q, p.k, p.index_offset,
                  p.out_scores, p.out_idx, p.out_stride,
                  static_cast<int>(blockIdx.x) * (NUM_THREADS / 32) + warp,
@@ -823,7 +838,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   if (threadIdx.x == 0) {
     trace_stamp(p, 5);                                       // exit
-    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + 7] = clock64();
+    if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * TRACE_SLOTS + 7] = clock64();
   }
 }
 

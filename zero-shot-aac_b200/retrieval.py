@@ -300,7 +300,7 @@ class RelatedBank:
         return a.value, b.value, c.value
 
     def trace(self, stamps: Optional[torch.Tensor]) -> None:
-        """Per-CTA %globaltimer stamps of the fused kernel into a uint64-sized [ctas, 8] int64
+        """Per-CTA %globaltimer stamps of the fused kernel into a uint64-sized [ctas, 16] int64
         tensor on this device (None switches tracing off).  Tuning hook."""
         self._trace_keepalive = stamps
         _abi.check(self._lib.zs_debug_trace(self._ctx, None if stamps is None else stamps.data_ptr()))
