@@ -32,7 +32,7 @@ def test_pipeline_and_generator_sharded_equal_single_gpu(tmp_path):
            os.path.join(ROOT, "tools", "dist_check_r2.py"), str(tmp_path)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("on all ranks: True") == 8
+    assert out.stdout.count("on all ranks: True") == 12
     assert out.stdout.count("identical to the single-GPU stream: True") == 2
 
 

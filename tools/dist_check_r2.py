@@ -60,10 +60,10 @@ def main():
     sb.upload_global(bank)
     torch.cuda.synchronize()
     for result in ("replicated", "row_slice"):
-        for from_host in (False, True):
+        for from_host, how in ((False, "full"), (True, "full"), (True, "replicate")):
             for rescore in (False, True):
                 pipe = SearchPipeline(sb, Q, k, depth=2, from_host=from_host, to_host=True, result=result,
-                                      rescore_from=bank[sb.lo:sb.hi] if rescore else None)
+                                      rescore_from=bank[sb.lo:sb.hi] if rescore else None, input=how)
                 slots = [pipe.submit(q_host if from_host else queries) for _ in range(3)]   # wraps around the 2 slots
                 pipe.wait_stream()
                 torch.cuda.synchronize()
@@ -78,7 +78,7 @@ def main():
                 good = all_ok(same, device)
                 ok &= good
                 if rank == 0:
-                    print(f"[dist_check_r2] pipeline result={result} from_host={from_host} rescore={rescore}: "
+                    print(f"[dist_check_r2] pipeline result={result} from_host={from_host} input={how} rescore={rescore}: "
                           f"bit-exact vs single GPU on all ranks: {good}", flush=True)
     whole.close()
     sb.local.close()

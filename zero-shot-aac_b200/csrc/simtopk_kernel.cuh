@@ -377,6 +377,7 @@ __device__ __noinline__ void solo_merge(const float* part_scores, const int* par
       out_idx[static_cast<size_t>(row) * out_stride + r] = (ix == SENT) ? -1ll : ix + index_offset;
     };
     if (n_lists <= 64) warp_merge_keys<2>(n_lists, k, lane, load_key, store);
+    else if (n_lists <= 256) warp_merge_keys<8>(n_lists, k, lane, load_key, store);
     else warp_merge_keys<16>(n_lists, k, lane, load_key, store);
   }
 }

@@ -244,7 +244,7 @@ def process_data(valid_text_embs: torch.Tensor, all_data: Iterable[dict], topnum
     helper = bank.local if world > 1 else bank
     pipe = SearchPipeline(bank, world * per, topnumber, depth=2, from_host=True, to_host=False,
                           result="row_slice", rescore_from=shard_f32 if rescore_fp32 else None,
-                          excludes_self=exclude_self)
+                          excludes_self=exclude_self, input="slice")
     # pinned staging, allocated once (page-locking costs more than the search); a step's buffers
     # are free again once its records have been yielded
     q_stage = [torch.zeros((world * per, d), dtype=torch.float32).pin_memory() for _ in range(2)]

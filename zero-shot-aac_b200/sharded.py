@@ -153,16 +153,23 @@ class ShardedRelatedBank:
 class SearchPipeline:
     """Software pipeline of searches against one (sharded) bank: three CUDA streams per rank.
 
-        input   : this rank's slice of the host query batch -> device (pinned H2D) and the
-                  all-gather that replicates the batch over NVLink            [batch i+1]
-        search  : normalise + cast -> fused similarity / top-k over the shard  [batch i]
-        output  : exchange of the shard-local lists, k-way merge, D2H          [batch i-1]
+        input   : the host query batch -> device, pinned H2D on the copy engine      [batch i+1]
+        search  : normalise + cast -> fused similarity / top-k over the shard ->
+                  exchange of the shard-local lists (NCCL) -> k-way merge            [batch i]
+        output  : merged rows -> pinned host memory, D2H on the copy engine          [batch i-1]
 
-    Every search of a sharded bank ends in an exchange + merge (and, end to end, begins with an
-    upload); issued on one stream those serialise with the fused kernel (1.6 ms of a 111 ms step
-    at 8 GPUs in round 1, 5 ms more end to end).  Here they run on side streams with `depth`
-    buffer sets, two extra NCCL communicators keep the input and output collectives independent
-    of each other, and the fused kernels of consecutive batches run back to back.
+    What overlaps is what the copy engines do.  The fused kernel is persistent — one CTA per SM,
+    all of the SM's registers — so nothing that needs SMs can run beside it: round 2 measured an
+    exchange + merge issued on a side stream under the next batch's kernel at 2 GPUs, and the NCCL
+    kernels (spinning on SMs until the slower rank arrives) kept part of the next grid from
+    starting, its lock-step windows timed out, and the step went from 446 to 602 ms
+    (profiles/r02/SUMMARY.md).  Collectives therefore stay on the search stream, between fused
+    kernels, where they cost their own ~1 ms; uploads and read-backs cost nothing.
+
+    Queries: input="replicate" uploads only this rank's 1/G slice and all-gathers the batch over
+    NVLink on the search stream (G x less PCIe traffic, ~0.5 ms of NVLink time per 268 MB);
+    input="full" (default when from_host) has every rank upload the whole batch over its own PCIe
+    link, which the copy engine hides entirely under the previous batch's kernel.
 
     result="replicated": all-gather + merge of all Q rows on every rank (what
     ShardedRelatedBank.search returns).  result="row_slice": rank r ends up with the global top-k
@@ -182,9 +189,13 @@ class SearchPipeline:
                  self_index: Optional[torch.Tensor] = None, normalize_queries: bool = True,
                  query_dtype: torch.dtype = torch.float32,
                  rescore_from: Optional[torch.Tensor] = None, rescore_margin: int = 8,
-                 excludes_self: bool = False):
+                 excludes_self: bool = False, input: str = "full"):
         if result not in ("replicated", "row_slice"):
             raise ValueError(f"result must be 'replicated' or 'row_slice', got {result!r}")
+        if input not in ("full", "replicate", "slice"):
+            raise ValueError(f"input must be 'full', 'replicate' or 'slice', got {input!r}")
+        # "slice": like "replicate", and only rows [lo, hi) of the host batch are meaningful
+        self.input = input
         self.sharded = isinstance(bank, ShardedRelatedBank)
         self.bank = bank
         self.local = bank.local if self.sharded else bank
@@ -210,13 +221,6 @@ class SearchPipeline:
         self.per = -(-q // G)                          # query rows per rank (input slices, row_slice results)
         self.lo = min(self.rank * self.per, q)
         self.hi = min(self.lo + self.per, q)
-        self.g_in = self.g_out = None
-        if G > 1:
-            ranks = list(range(dist.get_world_size(self.group)))
-            if self.group is not None:
-                ranks = dist.get_process_group_ranks(self.group)
-            self.g_in = dist.new_group(ranks)          # own communicators: the three stages' collectives
-            self.g_out = dist.new_group(ranks)         # must not queue behind one another
         self.s_in, self.s_main, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         rows_out = self.per if (result == "row_slice" and G > 1) else q
         self.rows_out = rows_out
@@ -243,7 +247,8 @@ class SearchPipeline:
             self.slots.append(slot)
         self.local.reserve(self.q, self.kc)
         self._next = 0
-        self.h2d_bytes = (self.hi - self.lo) * self.dim * torch.empty((), dtype=query_dtype).element_size() if from_host else 0
+        up_rows = q if input == "full" else (self.hi - self.lo)
+        self.h2d_bytes = up_rows * self.dim * torch.empty((), dtype=query_dtype).element_size() if from_host else 0
         self.d2h_bytes = rows_out * self.k * 12 if to_host else 0
 
     @property
@@ -267,6 +272,7 @@ class SearchPipeline:
         slot = self.slots[idx]
         cur = torch.cuda.current_stream(self.device)
         G = self.world
+        replicate = self.from_host and G > 1 and self.input != "full"
         if self.from_host:
             with torch.cuda.stream(self.s_in):
                 if slot["used"]:
@@ -274,11 +280,12 @@ class SearchPipeline:
                 else:
                     self.s_in.wait_stream(cur)
                 q_full = slot["q_full"]
-                mine = q_full[self.rank * self.per:(self.rank + 1) * self.per]
-                if self.hi > self.lo:
-                    mine[:self.hi - self.lo].copy_(queries[self.lo:self.hi], non_blocking=True)
-                if G > 1:
-                    dist.all_gather_into_tensor(q_full.view(-1), mine.reshape(-1), group=self.g_in)
+                if replicate:
+                    mine = q_full[self.rank * self.per:(self.rank + 1) * self.per]
+                    if self.hi > self.lo:
+                        mine[:self.hi - self.lo].copy_(queries[self.lo:self.hi], non_blocking=True)
+                else:
+                    q_full[:self.q].copy_(queries[:self.q], non_blocking=True)
                 slot["in_done"].record(self.s_in)
             q_dev = q_full[:self.q]
         else:
@@ -289,7 +296,10 @@ class SearchPipeline:
             elif not slot["used"]:
                 self.s_main.wait_stream(cur)
             if slot["used"]:
-                self.s_main.wait_event(slot["out_done"])          # local_s / local_i are free again
+                self.s_main.wait_event(slot["out_done"])          # result buffers are free again
+            if replicate:
+                mine = q_full[self.rank * self.per:(self.rank + 1) * self.per]
+                dist.all_gather_into_tensor(q_full.view(-1), mine.reshape(-1), group=self.group)
             if self.rescore_from is None:
                 self.local.search(q_dev, self.k, normalize_queries=self.normalize_queries,
                                   self_index=self_index,
@@ -300,25 +310,27 @@ class SearchPipeline:
                 self.local.rescore(q_dev, self.rescore_from, slot["cand_i"], self.k,
                                    normalize=self.normalize_queries, index_offset=self.local.index_offset,
                                    out=(slot["local_s"][:self.q], slot["local_i"][:self.q]))
-            slot["search_done"].record(self.s_main)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(slot["search_done"])
             if G == 1:
                 res_s, res_i = slot["local_s"][:self.q], slot["local_i"][:self.q]
             else:
                 if self.result == "row_slice":
-                    dist.all_to_all_single(slot["recv_s"].view(-1), slot["local_s"].view(-1), group=self.g_out)
-                    dist.all_to_all_single(slot["recv_i"].view(-1), slot["local_i"].view(-1), group=self.g_out)
+                    dist.all_to_all_single(slot["recv_s"].view(-1), slot["local_s"].view(-1), group=self.group)
+                    dist.all_to_all_single(slot["recv_i"].view(-1), slot["local_i"].view(-1), group=self.group)
                 else:
-                    dist.all_gather_into_tensor(slot["recv_s"].view(-1), slot["local_s"][:self.q].reshape(-1), group=self.g_out)
-                    dist.all_gather_into_tensor(slot["recv_i"].view(-1), slot["local_i"][:self.q].reshape(-1), group=self.g_out)
+                    dist.all_gather_into_tensor(slot["recv_s"].view(-1), slot["local_s"][:self.q].reshape(-1), group=self.group)
+                    dist.all_gather_into_tensor(slot["recv_i"].view(-1), slot["local_i"][:self.q].reshape(-1), group=self.group)
                 self.local.merge(slot["recv_s"], slot["recv_i"], out=(slot["out_s"], slot["out_i"]))
                 res_s, res_i = slot["out_s"], slot["out_i"]
-            if self.to_host:
+            slot["res"] = (res_s, res_i)
+            slot["search_done"].record(self.s_main)
+        if self.to_host:
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(slot["search_done"])
                 slot["host_s"].copy_(res_s, non_blocking=True)
                 slot["host_i"].copy_(res_i, non_blocking=True)
-            slot["out_done"].record(self.s_out)
-            slot["res"] = (res_s, res_i)
+                slot["out_done"].record(self.s_out)
+        else:
+            slot["out_done"].record(self.s_main)
         slot["keepalive"] = (queries, self_index)     # inputs of kernels still queued on the side streams
         slot["used"] = True
         return idx
