@@ -507,13 +507,23 @@ def run_cli(args, module: str, argv, load_fn) -> None:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    import time
+    t0 = time.perf_counter()
     valid_text_embs, all_data = load_fn(args.input_path)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     processed_data_gen = process_data(valid_text_embs, all_data, args.topnumber,
                                       exclude_self=args.exclude_self, rescore_fp32=args.rescore_fp32,
                                       dtype=args.dtype)
     total_items = len(all_data)
     save_data_to_hdf5(processed_data_gen, args.output_path, total_items, workers=args.writer_procs,
                       fast_pickle=args.fast_pickle)
+    t2 = time.perf_counter()
+    if os.environ.get("ZSAAC_TIMING") == "1" and int(os.environ.get("RANK", "0")) == 0:
+        import json
+        print(json.dumps({"zsaac_timing": {"records": total_items, "gpus": world_env,
+                                           "load_data_s": round(t1 - t0, 3),
+                                           "process_and_save_s": round(t2 - t1, 3)}}), flush=True)
     if world_env > 1:
         import torch.distributed as dist
         dist.barrier()
