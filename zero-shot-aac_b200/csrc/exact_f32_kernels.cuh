@@ -27,9 +27,8 @@
 namespace zs {
 
 constexpr int EXACT_THREADS = 256;
-constexpr int EXACT_RB = 4;                         // bank rows per warp
 constexpr int EXACT_QB = 4;                         // queries per register tile
-constexpr int EXACT_ROWS_PER_BLOCK = (EXACT_THREADS / 32) * EXACT_RB;   // 32
+constexpr int EXACT_SMALL_BANK = 8192;              // up to here: one bank row per warp (latency), else four
 constexpr int EXACT_FUSED_MAX_Q = 64;               // single-launch top-k up to this many queries
 
 // (s, i) ranks before (ts, ti) in the result order (score desc, index asc)
@@ -90,6 +89,11 @@ __device__ __forceinline__ void warp_topk_row(Load load, int64_t n, int k, long 
 
 constexpr int EXACT_STAGE_COLS = 1024;      // rows up to this long are staged in shared memory (per warp)
 
+// RB bank rows per warp: 4 for throughput on large problems (the rows are re-read from L1 for
+// every block of 4 queries), 1 for the small banks of the latency-bound callers (label bank, class
+// prompts: more CTAs, and the warp's row stays in registers).  D1024: d <= 1024, the embedding
+// loop is fully unrolled so that all loads of a query block are in flight together.
+template <int RB, bool D1024>
 __global__ void __launch_bounds__(EXACT_THREADS)
 exact_scores_kernel(const float* __restrict__ queries, int Q, const float* __restrict__ bank,
                     int64_t n_bank, int d, int normalize, float* scores,
@@ -98,48 +102,93 @@ exact_scores_kernel(const float* __restrict__ queries, int Q, const float* __res
                     long long index_offset, float* out_scores, long long* out_idx) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (EXACT_THREADS / 32) + warp) * EXACT_RB;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (EXACT_THREADS / 32) + warp) * RB;
+  constexpr int STEPS = D1024 ? 8 : 1;          // 128-element steps held in registers at once
   if (row0 < n_bank) {
-    const float* brow[EXACT_RB];
-    float norm_b[EXACT_RB];
+    const float* brow[RB];
+    float norm_b[RB];
 #pragma unroll
-    for (int r = 0; r < EXACT_RB; ++r)
+    for (int r = 0; r < RB; ++r)
       brow[r] = bank + min(row0 + r, n_bank - 1) * d;      // clamped: the duplicates are not stored
-    if (normalize) {
-      float bb[EXACT_RB] = {};
-      for (int e = lane * 4; e < d; e += 128) {
+    float4 breg[RB][STEPS];
+    if constexpr (D1024) {
 #pragma unroll
-        for (int r = 0; r < EXACT_RB; ++r) {
-          const float4 b = *reinterpret_cast<const float4*>(brow[r] + e);
-          bb[r] = fmaf(b.x, b.x, bb[r]); bb[r] = fmaf(b.y, b.y, bb[r]);
-          bb[r] = fmaf(b.z, b.z, bb[r]); bb[r] = fmaf(b.w, b.w, bb[r]);
+      for (int t = 0; t < STEPS; ++t) {
+        const int e = lane * 4 + t * 128;
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+          breg[r][t] = (e < d) ? *reinterpret_cast<const float4*>(brow[r] + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (normalize) {
+      float bb[RB] = {};
+      if constexpr (D1024) {
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const float4 b = breg[r][t];
+            bb[r] = fmaf(b.x, b.x, bb[r]); bb[r] = fmaf(b.y, b.y, bb[r]);
+            bb[r] = fmaf(b.z, b.z, bb[r]); bb[r] = fmaf(b.w, b.w, bb[r]);
+          }
+        }
+      } else {
+        for (int e = lane * 4; e < d; e += 128) {
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const float4 b = *reinterpret_cast<const float4*>(brow[r] + e);
+            bb[r] = fmaf(b.x, b.x, bb[r]); bb[r] = fmaf(b.y, b.y, bb[r]);
+            bb[r] = fmaf(b.z, b.z, bb[r]); bb[r] = fmaf(b.w, b.w, bb[r]);
+          }
         }
       }
 #pragma unroll
-      for (int r = 0; r < EXACT_RB; ++r) norm_b[r] = fmaxf(sqrtf(warp_sum(bb[r])), 1e-12f);
+      for (int r = 0; r < RB; ++r) norm_b[r] = fmaxf(sqrtf(warp_sum(bb[r])), 1e-12f);
     }
     for (int q0 = 0; q0 < Q; q0 += EXACT_QB) {
       const float* qrow[EXACT_QB];
 #pragma unroll
       for (int j = 0; j < EXACT_QB; ++j) qrow[j] = queries + static_cast<int64_t>(min(q0 + j, Q - 1)) * d;
-      float acc[EXACT_QB][EXACT_RB] = {};
+      float acc[EXACT_QB][RB] = {};
       float qq[EXACT_QB] = {};
-      for (int e = lane * 4; e < d; e += 128) {
-        float4 b[EXACT_RB];
-#pragma unroll
-        for (int r = 0; r < EXACT_RB; ++r) b[r] = *reinterpret_cast<const float4*>(brow[r] + e);
+      auto step = [&](const float4 (&b)[RB], const float4 (&a)[EXACT_QB]) {
 #pragma unroll
         for (int j = 0; j < EXACT_QB; ++j) {
-          const float4 a = *reinterpret_cast<const float4*>(qrow[j] + e);
           if (normalize) {
-            qq[j] = fmaf(a.x, a.x, qq[j]); qq[j] = fmaf(a.y, a.y, qq[j]);
-            qq[j] = fmaf(a.z, a.z, qq[j]); qq[j] = fmaf(a.w, a.w, qq[j]);
+            qq[j] = fmaf(a[j].x, a[j].x, qq[j]); qq[j] = fmaf(a[j].y, a[j].y, qq[j]);
+            qq[j] = fmaf(a[j].z, a[j].z, qq[j]); qq[j] = fmaf(a[j].w, a[j].w, qq[j]);
           }
 #pragma unroll
-          for (int r = 0; r < EXACT_RB; ++r) {
-            acc[j][r] = fmaf(a.x, b[r].x, acc[j][r]); acc[j][r] = fmaf(a.y, b[r].y, acc[j][r]);
-            acc[j][r] = fmaf(a.z, b[r].z, acc[j][r]); acc[j][r] = fmaf(a.w, b[r].w, acc[j][r]);
+          for (int r = 0; r < RB; ++r) {
+            acc[j][r] = fmaf(a[j].x, b[r].x, acc[j][r]); acc[j][r] = fmaf(a[j].y, b[r].y, acc[j][r]);
+            acc[j][r] = fmaf(a[j].z, b[r].z, acc[j][r]); acc[j][r] = fmaf(a[j].w, b[r].w, acc[j][r]);
           }
+        }
+      };
+      if constexpr (D1024) {
+        float4 a[STEPS][EXACT_QB];
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+          const int e = lane * 4 + t * 128;
+#pragma unroll
+          for (int j = 0; j < EXACT_QB; ++j)
+            a[t][j] = (e < d) ? *reinterpret_cast<const float4*>(qrow[j] + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+          float4 b[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) b[r] = breg[r][t];
+          step(b, a[t]);
+        }
+      } else {
+        for (int e = lane * 4; e < d; e += 128) {
+          float4 b[RB], a[EXACT_QB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) b[r] = *reinterpret_cast<const float4*>(brow[r] + e);
+#pragma unroll
+          for (int j = 0; j < EXACT_QB; ++j) a[j] = *reinterpret_cast<const float4*>(qrow[j] + e);
+          step(b, a);
         }
       }
 #pragma unroll
@@ -147,7 +196,7 @@ exact_scores_kernel(const float* __restrict__ queries, int Q, const float* __res
         float norm_q = 1.0f;
         if (normalize) norm_q = fmaxf(sqrtf(warp_sum(qq[j])), 1e-12f);
 #pragma unroll
-        for (int r = 0; r < EXACT_RB; ++r) {
+        for (int r = 0; r < RB; ++r) {
           float s = warp_sum(acc[j][r]);
           if (normalize) s = s / (norm_q * norm_b[r]);
           if (lane == 0 && q0 + j < Q && row0 + r < n_bank)

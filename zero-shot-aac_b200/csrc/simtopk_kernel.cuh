@@ -127,9 +127,10 @@ struct SimTopkParams {
   const float* bound_scores;     // nullable
   const long long* bound_idx;    // global indices
   long long bound_stride;
-  // Single-launch ("solo") mode for small searches: the kernel is launched cooperatively, casts
-  // (and normalises) the queries itself in a distributed prologue and merges the partial lists
-  // itself after a grid-wide arrival counter, so a search is ONE launch instead of three.
+  // Single-launch ("solo") mode for small searches: the kernel casts (and normalises) the queries
+  // itself in a distributed prologue and merges the partial lists itself after a grid-wide
+  // arrival counter, so a search is ONE launch instead of three.  Needs every CTA of the grid
+  // resident at once: at most one CTA per SM is launched (see launch_simtopk).
   int solo;
   const void* q_src;             // raw queries [Q, d] (nullptr: the bf16 workspace is already filled)
   int q_src_bf16;                // dtype of q_src
@@ -329,8 +330,8 @@ __device__ __noinline__ float boot_threshold(uint32_t taddr, int col_first, int 
 // ---------------------------------------------------------------------------------------------
 // Solo mode helpers
 // All lanes poll (one coalesced request per try); straight-line asm so that the callers keep
-// warp-uniform control flow.  Cooperative launch guarantees that every CTA of the grid is
-// resident, so the wait always ends; the bound only turns a bug into a trap.
+// warp-uniform control flow.  The grid has at most one CTA per SM, so every CTA becomes resident
+// and the wait ends; the bound (~a minute) only turns a bug into a trap.
 __device__ __forceinline__ void grid_wait(const unsigned long long* cnt, unsigned long long target,
                                           int* err, int code) {
   asm volatile(

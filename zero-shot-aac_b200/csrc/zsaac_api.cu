@@ -85,8 +85,9 @@ struct zs_ctx {
   unsigned int epoch = 0;                 // tags row_thr / boot entries; bumped per search pass
   unsigned long long* grid_cnt = nullptr; // [2] monotonic arrival counters of the single-launch mode
   unsigned long long cnt_base[2] = {0, 0};
-  int solo_state = 0;                     // 0 = not probed, 1 = cooperative launch works, -1 = unavailable
+  int solo_state = 0;                     // 0 = not probed, 1 = single-launch mode works, -1 = unavailable
   int solo_override = -1;                 // env ZSAAC_SOLO=0|1 (tests / A-B runs); -1 = choose per search
+  bool cooperative = false;               // env ZSAAC_COOPERATIVE=1: launch single-launch searches cooperatively
   int boot_override = -1;                 // env ZSAAC_BOOT=0|1: bootstrap off / on wherever it is valid; -1 = per search
   float* part_scores = nullptr;   // [chunks * EPI_HALVES, Q, k]
   int* part_idx = nullptr;
@@ -319,7 +320,14 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   cfg.stream = st;
   cudaLaunchAttribute attr[3];
   int n_attr = 0;
-  if (p.solo != 0) {     // grid-wide arrival counters inside the kernel: every CTA must be resident
+  // Single-launch mode waits on grid-wide arrival counters inside the kernel, so every CTA has to
+  // become resident while the others spin.  The grid never exceeds one CTA per SM (198 KiB of
+  // shared memory each), so on a GPU that is not running another spinning grid they all are;
+  // kernels of other streams only delay the last CTAs.  The cooperative-launch attribute would
+  // make that a guarantee, but profilers cannot replay cooperative cluster launches (ncu 2025.2:
+  // "LaunchFailed"), so it is opt-in (ZSAAC_COOPERATIVE=1); processes that run searches of one
+  // GPU concurrently from several streams should set it, or ZSAAC_SOLO=0.
+  if (p.solo != 0 && ctx->cooperative) {
     attr[n_attr].id = cudaLaunchAttributeCooperative;
     attr[n_attr].val.cooperative = 1;
     ++n_attr;
@@ -345,7 +353,7 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p);
     if (le != cudaSuccess && p.solo != 0) {
       cudaGetLastError();          // not sticky: the caller falls back to the three-launch path
-      return fail(ZS_ERR_STATE, "cooperative launch unavailable: %s", cudaGetErrorString(le));
+      return fail(ZS_ERR_STATE, "single-launch search could not be launched: %s", cudaGetErrorString(le));
     }
     if (le != cudaSuccess)
       return fail(ZS_ERR_CUDA, "cudaLaunchKernelEx(zs_simtopk_kernel) failed: %s", cudaGetErrorString(le));
@@ -433,9 +441,12 @@ int zs_create(zs_ctx** out, int device) {
   if (solo && (solo[0] == '0' || solo[0] == '1')) ctx->solo_override = solo[0] - '0';
   const char* boot = getenv("ZSAAC_BOOT");
   if (boot && (boot[0] == '0' || boot[0] == '1')) ctx->boot_override = boot[0] - '0';
-  int coop = 0;
-  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop)
-    ctx->solo_state = -1;
+  const char* coop_env = getenv("ZSAAC_COOPERATIVE");
+  if (coop_env && coop_env[0] == '1') {
+    int coop = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop)
+      ctx->cooperative = true;
+  }
   // the role code of a timed-out pipeline wait goes to mapped host memory, so that it can still
   // be read after the trap has poisoned the CUDA context
   e = cudaHostAlloc(&ctx->err_host, sizeof(int), cudaHostAllocMapped);
@@ -724,7 +735,7 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
       return ZS_OK;
     }
     if (rc != ZS_ERR_STATE) return rc;
-    ctx->solo_state = -1;        // cooperative launch refused: three launches from now on
+    ctx->solo_state = -1;        // launch refused: three launches from now on
     p.solo = 0;
     p.q_src = nullptr;
     p.grid_cnt = nullptr;
@@ -1012,6 +1023,25 @@ namespace {
 
 constexpr int64_t kExactMaxScores = 1ll << 30;    // 4 GiB of fp32 scores
 
+void launch_exact_scores(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
+                         int d, int normalize, int k_fused, const int64_t* self_index,
+                         int64_t index_offset, float* out_scores, int64_t* out_indices, cudaStream_t st) {
+  const bool small = n_rows <= zs::EXACT_SMALL_BANK;
+  const int rb = small ? 1 : 4;
+  const int rows_per_block = (zs::EXACT_THREADS / 32) * rb;
+  const unsigned blocks = static_cast<unsigned>((n_rows + rows_per_block - 1) / rows_per_block);
+  const long long* self = reinterpret_cast<const long long*>(self_index);
+  long long* out_i = reinterpret_cast<long long*>(out_indices);
+#define ZS_EXACT_LAUNCH(RB, D1024)                                                                 \
+  zs::exact_scores_kernel<RB, D1024><<<blocks, zs::EXACT_THREADS, 0, st>>>(                          \
+      queries, static_cast<int>(Q), bank, n_rows, d, normalize, ctx->exact_scores, ctx->exact_counter, \
+      k_fused, self, index_offset, out_scores, out_i)
+  if (small && d <= 1024) ZS_EXACT_LAUNCH(1, true);
+  else if (small) ZS_EXACT_LAUNCH(1, false);
+  else ZS_EXACT_LAUNCH(4, false);
+#undef ZS_EXACT_LAUNCH
+}
+
 int exact_prepare(zs_ctx* ctx, const char* fn, const float* queries, int64_t Q, const float* bank,
                   int64_t n_rows, int d) {
   if (Q < 0 || n_rows < 1) return fail(ZS_ERR_INVALID, "%s: Q=%lld n_rows=%lld", fn, (long long)Q, (long long)n_rows);
@@ -1050,12 +1080,9 @@ int zs_exact_topk_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float*
   if (rc || Q == 0) return rc;
   if (!out_scores || !out_indices) return fail(ZS_ERR_INVALID, "zs_exact_topk_f32: null output pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned blocks = static_cast<unsigned>((n_rows + zs::EXACT_ROWS_PER_BLOCK - 1) / zs::EXACT_ROWS_PER_BLOCK);
   const bool fused = Q <= zs::EXACT_FUSED_MAX_Q;     // one launch: the last block selects
-  zs::exact_scores_kernel<<<blocks, zs::EXACT_THREADS, 0, st>>>(
-      queries, static_cast<int>(Q), bank, n_rows, d, normalize, ctx->exact_scores, ctx->exact_counter,
-      fused ? k : 0, reinterpret_cast<const long long*>(self_index), index_offset, out_scores,
-      reinterpret_cast<long long*>(out_indices));
+  launch_exact_scores(ctx, queries, Q, bank, n_rows, d, normalize, fused ? k : 0, self_index, index_offset,
+                      out_scores, out_indices, st);
   ZS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   if (!fused) {
@@ -1078,10 +1105,7 @@ int zs_exact_rank_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float*
   if (rc || Q == 0) return rc;
   if (!target_index || !out_ranks) return fail(ZS_ERR_INVALID, "zs_exact_rank_f32: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned blocks = static_cast<unsigned>((n_rows + zs::EXACT_ROWS_PER_BLOCK - 1) / zs::EXACT_ROWS_PER_BLOCK);
-  zs::exact_scores_kernel<<<blocks, zs::EXACT_THREADS, 0, st>>>(
-      queries, static_cast<int>(Q), bank, n_rows, d, normalize, ctx->exact_scores, ctx->exact_counter, 0,
-      nullptr, 0ll, nullptr, nullptr);
+  launch_exact_scores(ctx, queries, Q, bank, n_rows, d, normalize, 0, nullptr, 0, nullptr, nullptr, st);
   ZS_CUDA(cudaGetLastError());
   const int64_t n_pairs = Q * n_targets;
   zs::exact_rank_kernel<<<static_cast<unsigned>((n_pairs * 32 + 255) / 256), 256, 0, st>>>(
