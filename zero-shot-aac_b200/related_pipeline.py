@@ -417,9 +417,10 @@ def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, tota
     (_FastTensorPickler): ~3x faster to write and ~4x faster to read back, same objects after
     pickle.load, different bytes on disk.
     Multi-GPU mode: every rank writes the records it processed (process_data yields only those)
-    to `<output_path>.rank<r>`; after a barrier rank 0 appends the rank files, in rank order, to
-    output_path — the same stream one GPU writes — and removes them.  The G ranks pickle in
-    parallel, which is what makes the script scale (pickling, not the search, is the wall clock)."""
+    to `<output_path>.rank<r>`, the sizes are exchanged, and every rank copies its file to its own
+    offset of output_path (rank order = item order: the same stream one GPU writes; an existing
+    file is appended to, like the reference's 'ab').  The G ranks pickle and copy in parallel,
+    which is what makes the script scale (pickling, not the search, is the wall clock)."""
     import os
     import shutil
     if workers is None:
@@ -431,14 +432,20 @@ def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, tota
         part = f"{output_path}.rank{rank:03d}"
         first, last = item_range(total_items, rank, world)
         _write_stream(processed_data_gen, part, "wb", last - first, workers, fast_pickle)
-        dist.barrier()
+        # every rank copies its own file to its own offset of the output (appended after whatever
+        # the file already holds, like the reference's 'ab'): the G copies run in parallel
+        sizes = [None] * world
+        dist.all_gather_object(sizes, os.path.getsize(part))
+        base = [0]
         if rank == 0:
+            base[0] = os.path.getsize(output_path) if os.path.exists(output_path) else 0
             with open(output_path, "ab") as out:
-                for r in range(world):
-                    piece = f"{output_path}.rank{r:03d}"
-                    with open(piece, "rb") as src:
-                        shutil.copyfileobj(src, out, length=64 << 20)
-                    os.remove(piece)
+                out.truncate(base[0] + sum(sizes))
+        dist.broadcast_object_list(base, src=0)
+        with open(part, "rb") as src, open(output_path, "r+b") as out:
+            out.seek(base[0] + sum(sizes[:rank]))
+            shutil.copyfileobj(src, out, length=64 << 20)
+        os.remove(part)
         dist.barrier()
         return
     _write_stream(processed_data_gen, output_path, "ab", total_items, workers, fast_pickle)
