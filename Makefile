@@ -12,7 +12,7 @@ all: lib
 
 lib: $(LIB)
 
-$(LIB): $(CSRC)/zsaac_api.cu $(CSRC)/memproj_kernel.cuh $(CSRC)/simtopk_kernel.cuh $(CSRC)/aux_kernels.cuh $(CSRC)/exact_f32_kernels.cuh $(CSRC)/ptx_sm100.cuh include/zsaac.h
+$(LIB): $(CSRC)/zsaac_api.cu $(CSRC)/memproj_kernel.cuh $(CSRC)/memproj_tc_kernels.cuh $(CSRC)/simtopk_kernel.cuh $(CSRC)/aux_kernels.cuh $(CSRC)/exact_f32_kernels.cuh $(CSRC)/ptx_sm100.cuh include/zsaac.h
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(NVCCFLAGS) $(EXTRA_NVCCFLAGS) -o $@ $(CSRC)/zsaac_api.cu
 

@@ -156,6 +156,21 @@ int zs_exact_rank_f32(zs_ctx* ctx, const float* queries, int64_t Q, const float*
                       int d, int normalize, const int64_t* target_index, int n_targets,
                       int64_t index_offset, float* out_target_scores, int64_t* out_ranks, void* stream);
 
+/* The same projection for BATCHES of queries on the tensor cores (Q >= 8 is where it beats the
+ * streaming pass per query above).  Both contractions — S = Q B^T and O = softmax(t S) B — run on
+ * the fused kernel's TMA + tcgen05 pipeline with every operand split into two bf16 terms
+ * (x = hi + lo; three products per contraction via a 3x longer K), which keeps the scores within
+ * ~1e-6 of fp32; the second contraction is split along K = bank rows into chunks of <= 32,768
+ * terms that are summed in fp32.
+ *   zs_memory_bank_prepare    splits the fp32 bank [n_rows, d] (d a multiple of 64) into the two
+ *                             operand layouts (12 n_rows d bytes, library-owned); once per bank
+ *   zs_memory_project_batched queries [Q, d] fp32 -> out [Q, d] fp32 unit rows
+ * Scratch per call (library-owned, grown on demand): 4 Q n_rows bytes of scores and 6 Q n_rows
+ * bytes of weights. */
+int zs_memory_bank_prepare(zs_ctx* ctx, const float* bank, int64_t n_rows, int d, void* stream);
+int zs_memory_project_batched(zs_ctx* ctx, const float* queries, int64_t Q, float temperature, float* out,
+                              void* stream);
+
 /* k-way merge of S sorted top-k lists per query (shard-local results gathered from S GPUs, or
  * bank chunks) under the total order (score desc, index asc).
  *   scores  list s of query q starts at scores  + s*score_stride + q*k   (float elements)

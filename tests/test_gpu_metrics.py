@@ -130,7 +130,10 @@ def test_map2memory_matches_reference_golden(name, tmp_path):
     assert mem.is_cuda and (mem.cpu() - torch.from_numpy(g["memory"])).abs().max().item() < 1e-6
 
 
-@pytest.mark.parametrize("Q,N,d", [(1, 400_000, 1024), (3, 50_001, 1024), (9, 1000, 512), (2, 7, 64)])
+@pytest.mark.parametrize("Q,N,d", [(1, 400_000, 1024), (3, 50_001, 1024), (9, 1000, 512), (2, 7, 64),
+                                   # batches: both contractions on the tensor cores (split-bf16 operands)
+                                   (8, 50_001, 1024), (64, 400_000, 1024), (130, 30_000, 1024),
+                                   (300, 5_000, 256), (1045, 19_195, 1024), (16, 63, 64)])
 def test_map2memory_against_oracle_at_scale(Q, N, d):
     import zsaac_b200  # noqa: F401
     from zsaac_b200.predict_prompt import map2memory
@@ -138,7 +141,13 @@ def test_map2memory_against_oracle_at_scale(Q, N, d):
     bank = torch.nn.functional.normalize(torch.randn(N, d, device="cuda", generator=gen), dim=-1)
     q = torch.nn.functional.normalize(torch.randn(Q, d, device="cuda", generator=gen), dim=-1)
     q[0] = torch.nn.functional.normalize(bank[N // 2] + 0.02 * q[0], dim=-1)     # one peaked query
+    if Q > 4:
+        q[1] = torch.nn.functional.normalize(bank[3] + bank[N // 3] + 0.01 * q[1], dim=-1)   # two near-equal peaks
     out = map2memory(q, bank)
     torch.cuda.synchronize()
     want = oracle.map2memory(q.cpu(), bank.cpu())
     assert (out.cpu() - want).abs().max().item() < 5e-5
+    assert (out.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    out2 = map2memory(q, bank)                       # second call: cached operands, same bits
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)

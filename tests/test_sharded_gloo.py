@@ -99,3 +99,47 @@ def test_sharded_search_world2_gloo(tmp_path, exclude_self):
     a = torch.load(tmp_path / "rank0.pt")
     b = torch.load(tmp_path / "rank1.pt")
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])     # every rank holds the result
+
+
+def _writer_worker(rank, world, port, n_items, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import zsaac_b200  # noqa: F401
+        from zsaac_b200 import related_pipeline as rp
+        first, last = rp.item_range(n_items, rank, world)
+        # what process_data yields on this rank in multi-GPU mode: its contiguous block of items
+        mine = ({"text_id": i, "related_embeddings": torch.full((2, 4), float(i))} for i in range(first, last))
+        rp.save_data_to_hdf5(mine, out_path, n_items)
+        assert not os.path.exists(f"{out_path}.rank{rank:03d}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_items", [(2, 11), (3, 3), (2, 1)])
+def test_multi_rank_writer_emits_the_single_gpu_stream(tmp_path, world, n_items):
+    """save_data_to_hdf5 with a process group up (reference :30-34 on N GPUs): every rank writes
+    the block of records it processed, the rank files land at their offsets of the output, which
+    is appended to like the reference's 'ab' — record order = item order."""
+    import pickle
+    out = tmp_path / "out.pkl"
+    with open(out, "wb") as f:
+        pickle.dump({"text_id": -1}, f)                    # the file already holds a record
+    mp.spawn(_writer_worker, args=(world, _free_port(), n_items, str(out)), nprocs=world, join=True)
+    got = []
+    with open(out, "rb") as f:
+        while True:
+            try:
+                got.append(pickle.load(f))
+            except EOFError:
+                break
+    assert [g["text_id"] for g in got] == [-1] + list(range(n_items))
+    assert all(torch.equal(g["related_embeddings"], torch.full((2, 4), float(g["text_id"]))) for g in got[1:])
+    sys.path.insert(0, ROOT)
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.related_pipeline import item_range
+    ranges = [item_range(n_items, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_items
+    assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))

@@ -46,6 +46,8 @@ SIGNATURES = {
     "zs_search": (_int, [_c_ctx, _ptr, _i64, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr]),
     "zs_rank_count": (_int, [_c_ctx, _ptr, _i64, _int, _int, _ptr, _int, _i64, _ptr, _ptr, _ptr]),
     "zs_memory_project": (_int, [_c_ctx, _ptr, _i64, _ptr, _i64, _int, ctypes.c_float, _ptr, _ptr]),
+    "zs_memory_bank_prepare": (_int, [_c_ctx, _ptr, _i64, _int, _ptr]),
+    "zs_memory_project_batched": (_int, [_c_ctx, _ptr, _i64, ctypes.c_float, _ptr, _ptr]),
     "zs_merge": (_int, [_c_ctx, _ptr, _ptr, _int, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr]),
     "zs_rescore_f32": (_int, [_c_ctx, _ptr, _i64, _int, _ptr, _i64, _int, _i64, _ptr, _int, _int,
                               _ptr, _ptr, _ptr]),

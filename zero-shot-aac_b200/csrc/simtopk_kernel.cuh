@@ -78,7 +78,12 @@ struct SimTopkParams {
   long long index_offset;       // global index of bank row 0 of this shard
   float* part_scores;    // [num_chunks * EPI_HALVES, Q, k]
   int* part_idx;         // [num_chunks * EPI_HALVES, Q, k]  column within the shard
-  float* dump;           // DUMP mode: [Q, n_bank]
+  float* dump;           // DUMP mode: [Q, n_bank] (or [k chunks, Q, n_bank] partial sums with kb_per_unit > 0)
+  // DUMP mode as a split-K GEMM (the batched memory projection's second contraction, K = bank
+  // rows): with kb_per_unit > 0 a "chunk" of the unit list is (bank tile, K chunk) — chunk =
+  // k_chunk * num_n_tiles + n_tile — and the unit accumulates only K blocks
+  // [k_chunk * kb_per_unit, +kb_per_unit) of that one tile into dump[k_chunk].
+  int kb_per_unit;
   // RANK mode: per (row, target) the target's score and column within the shard (-1 = unused),
   // and the per-(chunk, half) partial counts
   const float* tgt_scores;   // [Q, n_targets]
@@ -389,6 +394,26 @@ __device__ __noinline__ void solo_merge(const float* part_scores, const int* par
 // the reference's retrieval metrics obtain from a full argsort (retrieval/tools/utils.py:183,236).
 enum : int { MODE_TOPK = 0, MODE_DUMP = 1, MODE_RANK = 2 };
 
+// Tile and K-block ranges of a work unit's chunk (see SimTopkParams::kb_per_unit).
+struct UnitRange { int t0, t1, kb0, kb1, k_chunk; };
+__device__ __forceinline__ UnitRange unit_range(const SimTopkParams& p, int chunk) {
+  UnitRange r;
+  if (p.kb_per_unit > 0) {
+    r.k_chunk = chunk / p.num_n_tiles;
+    r.t0 = chunk - r.k_chunk * p.num_n_tiles;
+    r.t1 = r.t0 + 1;
+    r.kb0 = r.k_chunk * p.kb_per_unit;
+    r.kb1 = min(r.kb0 + p.kb_per_unit, p.num_k_blocks);
+  } else {
+    r.k_chunk = 0;
+    r.t0 = chunk * p.tiles_per_chunk;
+    r.t1 = min(r.t0 + p.tiles_per_chunk, p.num_n_tiles);
+    r.kb0 = 0;
+    r.kb1 = p.num_k_blocks;
+  }
+  return r;
+}
+
 template <int KCAP, int CG, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -527,8 +552,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int u = worker; u < num_units; u += num_workers, ++iter) {
       const int m_tile = u % p.num_m_tiles;
       const int chunk = u / p.num_m_tiles;
-      const int t0 = chunk * p.tiles_per_chunk;
-      const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+      const UnitRange ur = unit_range(p, chunk);
+      const int t0 = ur.t0, t1 = ur.t1;
       const int q_row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M;
       for (int t = t0; t < t1; ++t) {
         const int b_row = t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
@@ -547,7 +572,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (__shfl_sync(0xffffffffu, in_step, 0) == 0) sync_wait = false;
           }
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = ur.kb0; kb < ur.kb1; ++kb) {
           // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
           //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
           //  only look-ahead)
@@ -596,15 +621,15 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint32_t tile_count = 0;
       for (int u = worker; u < num_units; u += num_workers) {
         const int chunk = u / p.num_m_tiles;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+        const UnitRange ur = unit_range(p, chunk);
+        const int t0 = ur.t0, t1 = ur.t1;
         for (int t = t0; t < t1; ++t, ++tile_count) {
           const uint32_t acc = tile_count & 1u;
           const uint32_t acc_phase = (tile_count >> 1) & 1u;
           ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, ERR_MMA_TEMPTY);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          for (int kb = ur.kb0; kb < ur.kb1; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase, p.err_flag, ERR_MMA_FULL);
             ptx::tc_fence_after();
             const uint32_t a_src = base_u32 + stage * STAGE_STRIDE;
@@ -615,7 +640,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
                 ptx::umma_bf16<CG>(tmem_d, a_desc + 2u * k, b_desc + 2u * k, IDESC,
-                                   static_cast<uint32_t>((kb | k) != 0));
+                                   static_cast<uint32_t>(kb != ur.kb0 || k != 0));
               }
               if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
               else ptx::umma_commit_cg2(empty_bar(stage), 0b11);
@@ -641,8 +666,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int u = worker; u < num_units; u += num_workers) {
       const int m_tile = u % p.num_m_tiles;
       const int chunk = u / p.num_m_tiles;
-      const int t0 = chunk * p.tiles_per_chunk;
-      const int t1 = min(t0 + p.tiles_per_chunk, p.num_n_tiles);
+      const UnitRange ur = unit_range(p, chunk);
+      const int t0 = ur.t0, t1 = ur.t1;
       const int row = (m_tile * CG + static_cast<int>(cta_rank)) * BLOCK_M + row_in_tile;
       int self_col = -1;
       if (MODE == MODE_TOPK && p.self_index != nullptr && row < p.Q) {
@@ -724,7 +749,7 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n_bank)
-                  p.dump[static_cast<size_t>(row) * p.n_bank + col0 + j] = __uint_as_float(r[j]);
+                  p.dump[(static_cast<size_t>(ur.k_chunk) * p.Q + row) * p.n_bank + col0 + j] = __uint_as_float(r[j]);
             }
           } else if constexpr (RANK) {
             if (col0 + 32 <= p.n_bank) {

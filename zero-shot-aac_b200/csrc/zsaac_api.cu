@@ -20,6 +20,7 @@
 #include "aux_kernels.cuh"
 #include "exact_f32_kernels.cuh"
 #include "memproj_kernel.cuh"
+#include "memproj_tc_kernels.cuh"
 #include "simtopk_kernel.cuh"
 
 namespace {
@@ -100,6 +101,16 @@ struct zs_ctx {
   int64_t tgt_elems = 0, count_elems = 0;
   float* memproj_partials = nullptr;  // zs_memory_project: [blocks, 2, d + 4]
   int64_t memproj_elems = 0;
+  // batched memory projection on the tensor cores (zs_memory_bank_prepare / zs_memory_project_batched)
+  __nv_bfloat16* mp_bank = nullptr;    // B'   [n, 3d]      bank rows, B side [hi | hi | lo]
+  __nv_bfloat16* mp_bank_t = nullptr;  // Bt'' [d, 3 n_pad] bank transposed, B side
+  int64_t mp_rows = 0, mp_pad = 0;
+  int mp_d = 0;
+  __nv_bfloat16* mp_q = nullptr;       // Q'   [q_pad, 3d]      A side [hi | lo | hi]
+  float* mp_scores = nullptr;          // S    [Q, n]
+  __nv_bfloat16* mp_p = nullptr;       // P''  [q_pad, 3 n_pad] A side
+  float* mp_partial = nullptr;         // [k chunks, Q, d]
+  int64_t mp_q_rows = 0, mp_partial_elems = 0;
   unsigned int* sync_cnt = nullptr;   // lock-step window counters (see SimTopkParams)
   int64_t sync_cnt_elems = 0;
   float* exact_scores = nullptr;      // zs_exact_*: [Q, n_rows] fp32 score scratch
@@ -118,7 +129,7 @@ struct zs_ctx {
 
 namespace {
 
-int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int d,
+int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t d,
                     int box_rows) {
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * 2};
@@ -129,8 +140,8 @@ int encode_rows_map(zs_ctx* ctx, CUtensorMap* map, const void* base, int64_t row
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d box=%d)",
-                static_cast<int>(r), static_cast<long long>(rows), d, box_rows);
+    return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%lld box=%d)",
+                static_cast<int>(r), static_cast<long long>(rows), static_cast<long long>(d), box_rows);
   return ZS_OK;
 }
 
@@ -304,8 +315,8 @@ cudaError_t launch_merge(const float* scores, const IdxT* idx, int S, int64_t sc
 }
 
 template <int KCAP, int CG, int MODE>
-int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
-                   cudaStream_t st) {
+int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const CUtensorMap& bmap, const zs::SimTopkParams& p,
+                   int ctas, cudaStream_t st) {
   auto kern = zs::zs_simtopk_kernel<KCAP, CG, MODE>;
   const int smem = zs::smem_bytes<CG>();
   static bool smem_opt_in[64] = {};   // per instantiation and device: opt in to > 48 KiB once
@@ -350,7 +361,7 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
   const int slot = ctx->prof_count % ZS_PROFILE_RING;
   if (prof) ZS_CUDA(cudaEventRecord(ctx->prof_ev[2 * slot], st));
   {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, qmap, ctx->bank_map[CG - 1], p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, qmap, bmap, p);
     if (le != cudaSuccess && p.solo != 0) {
       cudaGetLastError();          // not sticky: the caller falls back to the three-launch path
       return fail(ZS_ERR_STATE, "single-launch search could not be launched: %s", cudaGetErrorString(le));
@@ -368,17 +379,18 @@ int launch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams
 
 template <int CG>
 int dispatch_simtopk(zs_ctx* ctx, const CUtensorMap& qmap, const zs::SimTopkParams& p, int ctas,
-                     bool dump, cudaStream_t st) {
-  if (dump) return launch_simtopk<8, CG, zs::MODE_DUMP>(ctx, qmap, p, ctas, st);
+                     bool dump, cudaStream_t st, const CUtensorMap* bank_map = nullptr) {
+  const CUtensorMap& bmap = bank_map ? *bank_map : ctx->bank_map[CG - 1];
+  if (dump) return launch_simtopk<8, CG, zs::MODE_DUMP>(ctx, qmap, bmap, p, ctas, st);
   if (p.part_counts != nullptr)   // rank mode: KCAP = target slots
-    return p.n_targets <= 1 ? launch_simtopk<1, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st)
-                            : launch_simtopk<8, CG, zs::MODE_RANK>(ctx, qmap, p, ctas, st);
+    return p.n_targets <= 1 ? launch_simtopk<1, CG, zs::MODE_RANK>(ctx, qmap, bmap, p, ctas, st)
+                            : launch_simtopk<8, CG, zs::MODE_RANK>(ctx, qmap, bmap, p, ctas, st);
   switch (kcap_for(p.k)) {
-    case 8: return launch_simtopk<8, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
-    case 12: return launch_simtopk<12, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
-    case 16: return launch_simtopk<16, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
-    case 24: return launch_simtopk<24, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
-    default: return launch_simtopk<32, CG, zs::MODE_TOPK>(ctx, qmap, p, ctas, st);
+    case 8: return launch_simtopk<8, CG, zs::MODE_TOPK>(ctx, qmap, bmap, p, ctas, st);
+    case 12: return launch_simtopk<12, CG, zs::MODE_TOPK>(ctx, qmap, bmap, p, ctas, st);
+    case 16: return launch_simtopk<16, CG, zs::MODE_TOPK>(ctx, qmap, bmap, p, ctas, st);
+    case 24: return launch_simtopk<24, CG, zs::MODE_TOPK>(ctx, qmap, bmap, p, ctas, st);
+    default: return launch_simtopk<32, CG, zs::MODE_TOPK>(ctx, qmap, bmap, p, ctas, st);
   }
 }
 
@@ -486,6 +498,12 @@ int zs_destroy(zs_ctx* ctx) {
   cudaFree(ctx->exact_scores);
   cudaFree(ctx->exact_counter);
   cudaFree(ctx->memproj_partials);
+  cudaFree(ctx->mp_bank);
+  cudaFree(ctx->mp_bank_t);
+  cudaFree(ctx->mp_q);
+  cudaFree(ctx->mp_scores);
+  cudaFree(ctx->mp_p);
+  cudaFree(ctx->mp_partial);
   cudaFree(ctx->tgt_scores);
   cudaFree(ctx->tgt_cols);
   cudaFree(ctx->part_counts);
@@ -929,6 +947,148 @@ int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float*
     ZS_CUDA(cudaGetLastError());
     ctx->launches += 3;
   }
+  return ZS_OK;
+}
+
+namespace {
+
+constexpr int kMemprojMaxKBlocksPerUnit = 512;     // 32,768 terms per tensor-memory accumulation
+
+// C[M, N] (+ K chunks) = A[M, K] . B[N, K]^T on the fused kernel's pipeline in DUMP mode.
+//   a      bf16 [a_rows_pad, K] (rows beyond `m` are padding, a_rows_pad a multiple of 256)
+//   b      bf16 [n, K]
+//   out    fp32 [k_chunks, m, n]: k_chunks = 1 unless split_k
+int run_dump_gemm(zs_ctx* ctx, const __nv_bfloat16* a, int64_t a_rows_pad, int64_t m, const __nv_bfloat16* b,
+                  int64_t n, int64_t K, bool split_k, float* out, int* k_chunks_out, cudaStream_t st) {
+  const int cg = m > zs::BLOCK_M ? 2 : 1;
+  const int workers = std::max(1, ctx->sm_count / cg);
+  zs::SimTopkParams p{};
+  p.Q = static_cast<int>(m);
+  p.n_bank = static_cast<int>(n);
+  p.num_k_blocks = static_cast<int>(K / zs::BLOCK_K);
+  p.num_m_tiles = static_cast<int>((m + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
+  p.num_n_tiles = static_cast<int>((n + zs::BLOCK_N - 1) / zs::BLOCK_N);
+  p.k = 1;
+  p.dump = out;
+  p.err_flag = ctx->err_flag;
+  int k_chunks = 1;
+  if (split_k) {
+    const int by_work = (workers + p.num_m_tiles * p.num_n_tiles - 1) / (p.num_m_tiles * p.num_n_tiles);
+    const int by_precision = (p.num_k_blocks + kMemprojMaxKBlocksPerUnit - 1) / kMemprojMaxKBlocksPerUnit;
+    k_chunks = std::max(1, std::min(p.num_k_blocks, std::max(by_work, by_precision)));
+    p.kb_per_unit = (p.num_k_blocks + k_chunks - 1) / k_chunks;
+    k_chunks = (p.num_k_blocks + p.kb_per_unit - 1) / p.kb_per_unit;
+    p.tiles_per_chunk = 1;
+    p.num_chunks = k_chunks * p.num_n_tiles;
+  } else {
+    p.tiles_per_chunk = std::max<int>(1, static_cast<int>((static_cast<int64_t>(p.num_n_tiles) * p.num_m_tiles + workers - 1) / workers));
+    p.num_chunks = (p.num_n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  }
+  if (k_chunks_out) *k_chunks_out = k_chunks;
+  const int64_t units = static_cast<int64_t>(p.num_m_tiles) * p.num_chunks;
+  const int ctas = static_cast<int>(std::min<int64_t>(units, workers)) * cg;
+  CUtensorMap amap, bmap;
+  int rc = encode_rows_map(ctx, &amap, a, a_rows_pad, K, zs::BLOCK_M);
+  if (rc) return rc;
+  rc = encode_rows_map(ctx, &bmap, b, n, K, zs::BLOCK_N / cg);
+  if (rc) return rc;
+  return cg == 2 ? dispatch_simtopk<2>(ctx, amap, p, ctas, true, st, &bmap)
+                 : dispatch_simtopk<1>(ctx, amap, p, ctas, true, st, &bmap);
+}
+
+}  // namespace
+
+int zs_memory_bank_prepare(zs_ctx* ctx, const float* bank, int64_t n_rows, int d, void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_memory_bank_prepare: ctx is null");
+  if (n_rows < 1 || n_rows > 0x3fffff00ll)
+    return fail(ZS_ERR_INVALID, "zs_memory_bank_prepare: n_rows=%lld", (long long)n_rows);
+  if (d < ZS_DIM_MULTIPLE || d % ZS_DIM_MULTIPLE != 0 || d > ZS_MAX_DIM)
+    return fail(ZS_ERR_INVALID, "zs_memory_bank_prepare: d=%d must be a multiple of %d in [%d, %d]", d,
+                ZS_DIM_MULTIPLE, ZS_DIM_MULTIPLE, ZS_MAX_DIM);
+  if (!bank) return fail(ZS_ERR_INVALID, "zs_memory_bank_prepare: bank is null");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_pad = (n_rows + zs::BLOCK_K - 1) / zs::BLOCK_K * zs::BLOCK_K;
+  if (ctx->mp_rows != n_rows || ctx->mp_d != d) {
+    if (ctx->mp_bank) { ZS_CUDA(cudaFree(ctx->mp_bank)); ctx->mp_bank = nullptr; }
+    if (ctx->mp_bank_t) { ZS_CUDA(cudaFree(ctx->mp_bank_t)); ctx->mp_bank_t = nullptr; }
+    if (ctx->mp_scores) { ZS_CUDA(cudaFree(ctx->mp_scores)); ctx->mp_scores = nullptr; }
+    if (ctx->mp_p) { ZS_CUDA(cudaFree(ctx->mp_p)); ctx->mp_p = nullptr; }
+    if (ctx->mp_q) { ZS_CUDA(cudaFree(ctx->mp_q)); ctx->mp_q = nullptr; }
+    ctx->mp_rows = 0;
+    ctx->mp_q_rows = 0;
+    ZS_CUDA(cudaMalloc(&ctx->mp_bank, static_cast<size_t>(n_rows) * 3 * d * sizeof(__nv_bfloat16)));
+    ZS_CUDA(cudaMalloc(&ctx->mp_bank_t, static_cast<size_t>(d) * 3 * n_pad * sizeof(__nv_bfloat16)));
+    ctx->mp_rows = n_rows;
+    ctx->mp_pad = n_pad;
+    ctx->mp_d = d;
+  }
+  zs::split_rows_kernel<<<static_cast<unsigned>((n_rows * 32 + 255) / 256), 256, 0, st>>>(
+      bank, ctx->mp_bank, n_rows, n_rows, d, zs::SPLIT_B_SIDE);
+  const dim3 tgrid(static_cast<unsigned>(n_pad / 32), static_cast<unsigned>((d + 31) / 32));
+  zs::transpose_split_kernel<<<tgrid, 256, 0, st>>>(bank, ctx->mp_bank_t, n_rows, n_pad, d);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+  return ZS_OK;
+}
+
+int zs_memory_project_batched(zs_ctx* ctx, const float* queries, int64_t Q, float temperature, float* out,
+                              void* stream) {
+  if (!ctx) return fail(ZS_ERR_INVALID, "zs_memory_project_batched: ctx is null");
+  ZS_CHECK_KERNEL_FLAG(ctx, "zs_memory_project_batched");
+  if (!ctx->mp_bank) return fail(ZS_ERR_STATE, "zs_memory_project_batched: call zs_memory_bank_prepare first");
+  if (Q < 0 || Q > 0x3fffff00ll) return fail(ZS_ERR_INVALID, "zs_memory_project_batched: Q=%lld", (long long)Q);
+  if (Q == 0) return ZS_OK;
+  if (!queries || !out) return fail(ZS_ERR_INVALID, "zs_memory_project_batched: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = ctx->mp_d;
+  const int64_t n = ctx->mp_rows, n_pad = ctx->mp_pad;
+  const int64_t q_pad = padded_query_rows(Q);
+  if (q_pad > ctx->mp_q_rows) {
+    if (ctx->mp_q) { ZS_CUDA(cudaFree(ctx->mp_q)); ctx->mp_q = nullptr; }
+    if (ctx->mp_scores) { ZS_CUDA(cudaFree(ctx->mp_scores)); ctx->mp_scores = nullptr; }
+    if (ctx->mp_p) { ZS_CUDA(cudaFree(ctx->mp_p)); ctx->mp_p = nullptr; }
+    ctx->mp_q_rows = 0;
+    ZS_CUDA(cudaMalloc(&ctx->mp_q, static_cast<size_t>(q_pad) * 3 * d * sizeof(__nv_bfloat16)));
+    ZS_CUDA(cudaMalloc(&ctx->mp_scores, static_cast<size_t>(q_pad) * n * sizeof(float)));
+    ZS_CUDA(cudaMalloc(&ctx->mp_p, static_cast<size_t>(q_pad) * 3 * n_pad * sizeof(__nv_bfloat16)));
+    // padding rows of P'' are never written again: zero them once
+    ZS_CUDA(cudaMemsetAsync(ctx->mp_p, 0, static_cast<size_t>(q_pad) * 3 * n_pad * sizeof(__nv_bfloat16), st));
+    ctx->mp_q_rows = q_pad;
+  }
+  // 1. queries -> A side [hi | lo | hi] (padding rows zero)
+  zs::split_rows_kernel<<<static_cast<unsigned>((q_pad * 32 + 255) / 256), 256, 0, st>>>(
+      queries, ctx->mp_q, Q, q_pad, d, zs::SPLIT_A_SIDE);
+  ZS_CUDA(cudaGetLastError());
+  // 2. S = Q . B^T  (K = 3d)
+  int rc = run_dump_gemm(ctx, ctx->mp_q, q_pad, Q, ctx->mp_bank, n, 3ll * d, false, ctx->mp_scores, nullptr, st);
+  if (rc) return rc;
+  // 3. P = softmax(t S), as the A side of the second contraction
+  zs::softmax_split_kernel<<<static_cast<unsigned>(Q), zs::SOFTMAX_THREADS, 0, st>>>(
+      ctx->mp_scores, ctx->mp_p, n, n_pad, temperature);
+  ZS_CUDA(cudaGetLastError());
+  // 4. O = P . B  (K = 3 n_pad, split into chunks) -> partial sums
+  const int n_tiles_out = (d + zs::BLOCK_N - 1) / zs::BLOCK_N;
+  const int m_tiles = static_cast<int>((Q + (Q > zs::BLOCK_M ? 2 : 1) * zs::BLOCK_M - 1) / ((Q > zs::BLOCK_M ? 2 : 1) * zs::BLOCK_M));
+  const int64_t kb_total = 3 * n_pad / zs::BLOCK_K;
+  const int64_t max_chunks = std::max<int64_t>((kb_total + kMemprojMaxKBlocksPerUnit - 1) / kMemprojMaxKBlocksPerUnit,
+                                               (ctx->sm_count + m_tiles * n_tiles_out - 1) / (m_tiles * n_tiles_out)) + 1;
+  const int64_t need = max_chunks * Q * d;
+  if (need > ctx->mp_partial_elems) {
+    if (ctx->mp_partial) { ZS_CUDA(cudaFree(ctx->mp_partial)); ctx->mp_partial = nullptr; ctx->mp_partial_elems = 0; }
+    ZS_CUDA(cudaMalloc(&ctx->mp_partial, static_cast<size_t>(need) * sizeof(float)));
+    ctx->mp_partial_elems = need;
+  }
+  int k_chunks = 1;
+  rc = run_dump_gemm(ctx, ctx->mp_p, q_pad, Q, ctx->mp_bank_t, d, 3 * n_pad, true, ctx->mp_partial, &k_chunks, st);
+  if (rc) return rc;
+  if (static_cast<int64_t>(k_chunks) * Q * d > ctx->mp_partial_elems)
+    return fail(ZS_ERR_STATE, "zs_memory_project_batched: partial buffer too small (%d chunks)", k_chunks);
+  // 5. sum the K chunks, L2-normalise
+  zs::memproj_reduce_kernel<<<static_cast<unsigned>(Q), 256, 0, st>>>(ctx->mp_partial, k_chunks, Q, d, out);
+  ZS_CUDA(cudaGetLastError());
+  ctx->launches += 3;
   return ZS_OK;
 }
 
