@@ -74,6 +74,11 @@ CASES = {
     "wavcaps_multi_dup": dict(seed=1003, n=72, k=3, dist="gauss", files=[40, 24, 8],
                               duplicates=[(50, 7), (71, 7)], module="wavcaps"),
     "generator_k1": dict(seed=1004, n=33, k=1, dist="gauss", files=[33], module="single"),
+    # --topnumber beyond one pass of the fused kernel (32), duplicates straddling the pass boundary
+    "generator_k40": dict(seed=1005, n=160, k=40, dist="gauss", files=[160],
+                          duplicates=[(150, 3), (151, 3), (152, 90)], module="single"),
+    "wavcaps_k70_clustered": dict(seed=1006, n=300, k=70, dist="clustered", centres=6, sigma=0.05,
+                                  files=[100, 200], module="wavcaps"),
 }
 
 
@@ -263,11 +268,16 @@ def run_memory_case(name, case):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])          # optional: regenerate just the named fixtures
     for n, c in MEMORY_CASES.items():
-        run_memory_case(n, c)
+        if not only or n in only:
+            run_memory_case(n, c)
     for n, c in RETRIEVAL_CASES.items():
-        run_retrieval_case(n, c)
+        if not only or n in only:
+            run_retrieval_case(n, c)
     for n, c in CASES.items():
-        run_generator_case(n, c)
+        if not only or n in only:
+            run_generator_case(n, c)
     for n, c in SEC_CASES.items():
-        run_sec_case(n, c)
+        if not only or n in only:
+            run_sec_case(n, c)

@@ -1,6 +1,7 @@
 """Randomised stress of the fused search against a torch restatement on the same GPU (run under
-gpurun).  Every case draws Q, N, k, forced chunk count, CTA-group, self-exclusion, normalisation,
-input dtype and a shard offset; the expectation multiplies the SAME bf16-rounded operands in fp32
+gpurun).  Every case draws Q, N, k (up to 200: several passes), forced chunk count, CTA-group,
+single-launch mode and threshold bootstrap (default / off / forced), self-exclusion,
+normalisation, input dtype and a shard offset; the expectation multiplies the SAME bf16-rounded operands in fp32
 (torch.matmul) and ranks under (score desc, index asc), so indices must agree wherever the
 expected scores are not within 1e-5 (relative to the row's largest |score|) of each other
 (accumulation order), and scores within the same bound.
@@ -28,7 +29,16 @@ for case in range(n_cases):
     Q = rng.choice([rng.randint(1, 40), rng.randint(40, 700), rng.randint(700, 3000)])
     d = rng.choice([64, 128, 256, 1024, 1024, 1024])
     excl = rng.random() < 0.3 and N > 1
-    k = rng.randint(1, min(32, N - (1 if excl else 0)))
+    # mostly one pass of the fused kernel (k <= 32), sometimes several (k up to 200)
+    k_max = min(32 if rng.random() < 0.75 else 200, N - (1 if excl else 0))
+    k = rng.randint(1, k_max)
+    # single-launch mode and the threshold bootstrap: library default, forced off, forced on
+    for var in ("ZSAAC_SOLO", "ZSAAC_BOOT"):
+        choice = rng.choice(["default", "0", "1"])
+        if choice == "default":
+            os.environ.pop(var, None)
+        else:
+            os.environ[var] = choice
     normalize = rng.random() < 0.7
     bf16_in = rng.random() < 0.25
     offset = rng.choice([0, 0, 12345, 10 ** 9])
@@ -81,6 +91,7 @@ for case in range(n_cases):
         print(f"   worst |score - expected| relative to the row's largest |score|: {rel:.2e}")
     if not ok or case % 25 == 0:
         print(f"case {case}: Q={Q} N={N} d={d} k={k} cg={cg} chunks={chunks} plan={rb.plan(Q, k)} "
+              f"solo={os.environ.get('ZSAAC_SOLO', 'default')} boot={os.environ.get('ZSAAC_BOOT', 'default')} "
               f"excl={excl} norm={normalize} bf16={bf16_in} off={offset} {kind} -> "
               f"{'ok' if ok else 'MISMATCH'} (scores {ok_s}, indices {ok_i}, sorted {ok_sorted}, "
               f"distinct {ok_distinct})", flush=True)

@@ -574,8 +574,8 @@ zs_simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         for (int kb = ur.kb0; kb < ur.kb1; ++kb) {
           // (an L2 prefetch of the next bank tile via cp.async.bulk.prefetch.tensor was measured
-          //  and halved the HBM-bound throughput — profiles/r01/SUMMARY.md — so the ring is the
-          //  only look-ahead)
+          //  twice: it halved the HBM-bound throughput in round 1 and cost 4-65 % on every small
+          //  shape in round 2 — profiles/r02/SUMMARY.md — so the ring is the only look-ahead)
           const bool bank_in_flight = issued < pre_issued;   // armed + bank half loaded in the prologue
           ++issued;
           if (!bank_in_flight) ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, ERR_PRODUCER);

@@ -381,16 +381,24 @@ def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str
                           fast: bool = False) -> None:
     """Pickle `items` in `workers` forked processes (pickling tensors is GIL-bound Python, ~80 us
     per record) and append the parts to `file` in order.  The bytes are exactly what the serial
-    loop would have written."""
+    loop would have written.  The children are forked per batch so that they see the batch through
+    copy-on-write memory (sending the records to a long-lived pool would cost the very pickling
+    this is meant to parallelise); they touch CPU tensors only, never CUDA.  Opt-in: forking a
+    multi-threaded process is at the caller's risk — `--gpus N` gets the same parallelism from
+    the N rank processes without forking."""
     import multiprocessing as mp
     import os
     import shutil
+    import tempfile
     global _WRITER_ITEMS, _WRITER_FAST
     _WRITER_ITEMS = items
     _WRITER_FAST = fast
     n = len(items)
     per = -(-n // workers)
-    jobs = [(lo, min(lo + per, n), f"{tmp_prefix}.part{j}") for j, lo in enumerate(range(0, n, per))]
+    # part files in a private directory next to the output (two jobs sharing an output prefix
+    # must not collide: ADVICE r1)
+    part_dir = tempfile.mkdtemp(prefix=".zsaac_parts_", dir=os.path.dirname(os.path.abspath(tmp_prefix)) or ".")
+    jobs = [(lo, min(lo + per, n), os.path.join(part_dir, f"part{j}")) for j, lo in enumerate(range(0, n, per))]
     try:
         # fork: children see the batch through copy-on-write memory; they only touch CPU tensors
         with mp.get_context("fork").Pool(len(jobs)) as pool:
@@ -400,9 +408,7 @@ def _write_batch_parallel(items: List[dict], file, workers: int, tmp_prefix: str
                 shutil.copyfileobj(src, file, length=16 << 20)
     finally:
         _WRITER_ITEMS = []
-        for _, _, part in jobs:
-            if os.path.exists(part):
-                os.remove(part)
+        shutil.rmtree(part_dir, ignore_errors=True)
 
 
 def save_data_to_hdf5(processed_data_gen: Iterable[dict], output_path: str, total_items: int,
