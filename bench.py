@@ -15,10 +15,14 @@ sampled queries are re-scored in fp32 against the whole (sharded) bank and north
 applied (|score - fp32| <= 1e-3; every returned index within 1e-3 of the fp32 k-th score; every
 clear fp32 winner returned); at N > 1 the merged result must be bit-identical on every rank and
 bit-identical to a single-GPU search of a 4,096-query slice.  A failed gate aborts non-zero.
-After the headline the other named shapes are timed as well (`workloads`): BASELINE configs
-1, 2, 3, 5 and the HBM-bound batches Q in {1, 32, 128} against the 400 k and 10 M banks, each with
-its own gate and roofline, next to the unfused library strawman (torch.matmul bf16 + topk) and
-the reference's literal per-item loop.
+The other named shapes are timed as well (`workloads`): BASELINE configs 1, 2, 3, 5 and the
+HBM-bound batches Q in {1, 32, 128} against the 400 k bank BEFORE the headline bank is built (they
+are searches of 50 us - 4 ms; right after the headline's seconds at the power cap they would be
+measured at the capped clock), Q in {1, 32, 128} against the resident 10 M bank after it — each
+with its own gate and roofline, next to the unfused library strawman (torch.matmul bf16 + topk)
+and the reference's literal per-item loop.  Sub-millisecond searches are repeated 50 times with
+the stream parked behind a spin kernel first, so the events bracket device time, not the host's
+launch latency.
 
 --impl reference times the reference's CPU formulation of the same path (torch fp32:
 F.normalize(q) @ bank.T -> topk, all host threads) on a bounded sample of the workload.
@@ -50,6 +54,7 @@ SMALL_Q = (1, 32, 128)      # HBM-bound batches, k = 10
 BANK_BLOCK = 65536          # rows per generation block; seed = bank_seed * 2**32 + block id
 L2_BYTES = 126 << 20        # B200 L2 capacity
 GATE_SAMPLES = 64
+SHORT_REPS = 50             # repetitions of a side shape whose search takes < 2 ms
 GATE_TOL = 1e-3             # north_star: scores within 1e-3 of fp32, index sets equal except near-ties
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -113,6 +118,13 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join(timeout=2)
+
+    def now(self):
+        """One reading of the SM clock (right after a short timed region, before the GPU idles down)."""
+        try:
+            return float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+        except Exception:
+            return None
 
     def report(self):
         if not self.samples:
@@ -278,22 +290,34 @@ def roofline_of(peaks, peaks_src, Q, shard_rows, k, k_ms, long_step):
 
 class Timer:
     """Event-timed steps: back to back when a step's inputs exceed L2, else an event pair per step
-    with a 256 MB write in between (L2 flush).  Max over ranks."""
+    with a 256 MB write in between (L2 flush).  Max over ranks.
+
+    `ahead_ms` > 0 (sub-millisecond shapes) first parks the stream behind a spin kernel of that
+    length, so that every launch of the timed region is already queued when the device gets to it:
+    the events then bracket device time only, not the host's launch latency (a search of 50-150 us
+    is shorter than the Python + ctypes call that enqueues it)."""
 
     def __init__(self, torch, dist, world, device):
         self.torch, self.dist, self.world, self.device = torch, dist, world, device
         self.flush_buf = None
+        self.samples = []          # per-step ms of the last flushed run (this rank)
 
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize(self.device)
 
-    def run(self, fn, steps, flush_l2, finish=None):
+    def park(self, ahead_ms):
+        if ahead_ms > 0:
+            self.torch.cuda._sleep(int(ahead_ms * 1.9e6))      # cycles at <= 1.9 GHz: at least ahead_ms
+
+    def run(self, fn, steps, flush_l2, finish=None, ahead_ms=0.0):
         torch = self.torch
         self.barrier()
+        self.samples = []
         if not flush_l2:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.park(ahead_ms)
             e0.record()
             for _ in range(steps):
                 fn()
@@ -306,6 +330,7 @@ class Timer:
             if self.flush_buf is None:
                 self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
             pairs = []
+            self.park(ahead_ms)
             for _ in range(steps):
                 self.flush_buf.zero_()                 # evicts bank, queries and outputs from L2
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,7 +341,8 @@ class Timer:
                 e1.record()
                 pairs.append((e0, e1))
             self.barrier()
-            total = sum(a.elapsed_time(b) for a, b in pairs)
+            self.samples = [a.elapsed_time(b) for a, b in pairs]
+            total = sum(self.samples)
         ms = torch.tensor([total], device=self.device)
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
@@ -490,20 +516,28 @@ def describe(w: Workload) -> str:
             + (", self-exclusion" if w.excl else ""))
 
 
-def time_side_workload(env, w: Workload, steps: int):
-    """Gate + device-resident timing of one of the extra shapes -> dict for `workloads`."""
+def time_side_workload(env, w: Workload, steps: int, when: str):
+    """Gate + device-resident timing of one of the extra shapes -> dict for `workloads`.
+    Sub-millisecond searches are repeated SHORT_REPS times behind a parked stream (Timer.run)."""
     torch, timer, peaks, peaks_src = env["torch"], env["timer"], env["peaks"], env["peaks_src"]
     gate = w.gate()
     for _ in range(3):
         w.search()
+    probe = timer.run(w.search, 3, w.flush_l2, ahead_ms=1.0) / 3
+    short = probe < 2.0
+    if short:
+        steps = SHORT_REPS
+    ahead = 2.0 if short else 0.0
     launches0 = w.local.launch_count
-    total = timer.run(w.search, steps, w.flush_l2)
+    total = timer.run(w.search, steps, w.flush_l2, ahead_ms=ahead)
+    per_step = sorted(timer.samples)
     launches = (w.local.launch_count - launches0) / steps
     ms = total / steps
-    # the fused kernel alone: a second, short pass with the library's own event pair around it
-    # (those events would sit between the launches of the timed pass)
+    sm_mhz = env["clock_now"]()
+    # the fused kernel alone: a second pass with the library's own event pair around it (those
+    # events would sit between the launches of the timed pass)
     w.local.profile(True)
-    timer.run(w.search, min(steps, 5), w.flush_l2)
+    timer.run(w.search, min(steps, 16), w.flush_l2, ahead_ms=ahead)
     kernel_ms = w.local.kernel_times_ms()
     w.local.profile(False)
     k_ms = statistics.mean(kernel_ms) if kernel_ms else ms
@@ -511,10 +545,78 @@ def time_side_workload(env, w: Workload, steps: int):
     roof["kernel_share_of_step"] = k_ms / ms
     # whole search (every launch of it, launch gaps included) against the same roofline
     whole = roofline_of(peaks, peaks_src, w.Q, w.hi - w.lo, w.k, ms, long_step=False)
-    return {"workload": describe(w), "ms_per_step": ms, "value": w.Q / (ms * 1e-3), "unit": "queries/s",
-            "steps": steps, "l2": "flushed between steps" if w.flush_l2 else "inputs larger than L2",
-            "launches_per_search": launches, "plan_chunks_tiles_ctas": list(w.local.plan(w.Q, w.k)),
-            "roofline": roof, "search_frac_of_roofline": whole["frac"], "parity_gate": gate}
+    out = {"workload": describe(w), "ms_per_step": ms, "value": w.Q / (ms * 1e-3), "unit": "queries/s",
+           "steps": steps, "l2": "flushed between steps" if w.flush_l2 else "inputs larger than L2",
+           "launches_per_search": launches, "plan_chunks_tiles_ctas": list(w.local.plan(w.Q, w.k)),
+           "roofline": roof, "search_frac_of_roofline": whole["frac"], "parity_gate": gate,
+           "measured": when, "sm_mhz_after": sm_mhz}
+    if per_step and env["world"] == 1:
+        out["ms_min_median_max"] = [per_step[0], statistics.median(per_step), per_step[-1]]
+    return out
+
+
+def side_named(env, head_name: str, steps: int):
+    """BASELINE configs other than the headline, each with its own bank, gate and roofline; config 3
+    also with the HBM-bound batches and the unfused library strawman.  Run BEFORE the headline bank
+    is built: these are searches of 50 us - 4 ms, and right after the headline's seconds at the
+    power cap the GPU still runs them at the capped clock (round 2: 0.31 vs 0.45 of roofline for the
+    same kernel at config 1), which says nothing about the shape itself."""
+    torch, timer, world, device = env["torch"], env["timer"], env["world"], env["device"]
+    out = []
+    side_steps = max(3, min(steps, 20))
+    for name in ("clotho_eval", "audiocaps", "wavcaps_400k", "allpairs_400k"):
+        if name == head_name:
+            continue
+        w = Workload(env, name)
+        out.append(time_side_workload(env, w, 3 if name == "allpairs_400k" else side_steps, "before the headline"))
+        if name == "wavcaps_400k":
+            for q_small in SMALL_Q:
+                ws = Workload(env, name, Q=q_small, k=10, bank=w.bank, label=f"{name}_q{q_small}")
+                out.append(time_side_workload(env, ws, side_steps, "before the headline"))
+            if world == 1:      # unfused library strawman on the same GPU, same operands
+                bank_bf16 = torch.empty(w.N, D, dtype=torch.bfloat16, device=device)
+                for row0, rows in bank_rows_fp32(torch, device, w.bank_seed, 0, w.N):
+                    bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
+                q_bf16 = torch.nn.functional.normalize(w.q_dev, dim=-1).bfloat16()
+
+                def straw():
+                    return strawman_topk(torch, q_bf16, bank_bf16, w.k)
+
+                for _ in range(2):
+                    straw()
+                st_ms = timer.run(straw, 3, False) / 3
+                out[-1 - len(SMALL_Q)]["strawman_torch_matmul_bf16_topk_ms"] = st_ms
+                del bank_bf16, q_bf16
+        w.close()
+        del w
+        torch.cuda.empty_cache()
+    return out
+
+
+def side_resident(env, head: Workload, steps: int):
+    """HBM-bound batches against the resident headline bank, and the strawman on a headline sample."""
+    torch, timer, world, device = env["torch"], env["timer"], env["world"], env["device"]
+    out = []
+    side_steps = max(3, min(steps, 20))
+    for q_small in SMALL_Q:
+        w = Workload(env, head.name, Q=q_small, k=10, bank=head.bank, label=f"{head.name}_q{q_small}")
+        out.append(time_side_workload(env, w, side_steps, "after the headline"))
+    if world == 1 and head.name == "synthetic_10m":
+        # (the [Q, N] fp32 score block of the whole batch does not fit: 1,024 queries)
+        n_q, N, k = 1024, head.N, head.k
+        bank_bf16 = torch.empty(N, D, dtype=torch.bfloat16, device=device)
+        for row0, rows in bank_rows_fp32(torch, device, head.bank_seed, 0, N):
+            bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
+        q_bf16 = torch.nn.functional.normalize(head.q_dev[:n_q], dim=-1).bfloat16()
+        strawman_topk(torch, q_bf16, bank_bf16, k)
+        st_ms = timer.run(lambda: strawman_topk(torch, q_bf16, bank_bf16, k), 2, False) / 2
+        ours_ms = timer.run(lambda: head.bank.search(head.q_dev[:n_q], k), 5, False) / 5
+        out.append({"workload": f"{head.name} sample: {n_q} queries vs {N}-row bank, top-{k}",
+                    "ms_per_step": ours_ms, "value": n_q / (ours_ms * 1e-3), "unit": "queries/s",
+                    "strawman_torch_matmul_bf16_topk_ms": st_ms})
+        del bank_bf16, q_bf16
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -540,9 +642,13 @@ def run_ours(args):
     peaks, peaks_src = load_peaks()
     timer = Timer(torch, dist, world, device)
     env = {"torch": torch, "dist": dist, "zs": zsaac_b200, "world": world, "rank": rank, "device": device,
-           "peaks": peaks, "peaks_src": peaks_src, "timer": timer}
+           "peaks": peaks, "peaks_src": peaks_src, "timer": timer, "clock_now": ClockSampler(local_rank).now}
     steps = args.steps
     warmup = max(args.warmup, 3)
+
+    # ---- the other named shapes first (short searches: measured before the headline heats the GPU)
+    workloads = []
+    workloads_named = [] if args.headline_only else side_named(env, args.workload, steps)
 
     # ---- headline workload: bank resident in HBM as bf16 before anything is timed
     head = Workload(env, args.workload, Q=args.queries or None, N=args.bank_rows or None)
@@ -639,54 +745,9 @@ def run_ours(args):
     except Exception:
         pass
 
-    # ---- the other named shapes (each gated, then timed; all sharded the same way at N > 1) ------
-    workloads = []
+    # ---- Q in {1, 32, 128} against the resident headline bank + the strawman on a headline sample
     if not args.headline_only:
-        side_steps = max(3, min(steps, 20))
-        for q_small in SMALL_Q:                                  # HBM-bound batches vs the resident bank
-            w = Workload(env, head.name, Q=q_small, k=10, bank=bank, label=f"{head.name}_q{q_small}")
-            workloads.append(time_side_workload(env, w, side_steps))
-        for name in ("clotho_eval", "audiocaps", "wavcaps_400k", "allpairs_400k"):
-            if name == head.name:
-                continue
-            w = Workload(env, name)
-            workloads.append(time_side_workload(env, w, 3 if name == "allpairs_400k" else side_steps))
-            if name == "wavcaps_400k":
-                for q_small in SMALL_Q:
-                    ws = Workload(env, name, Q=q_small, k=10, bank=w.bank, label=f"{name}_q{q_small}")
-                    workloads.append(time_side_workload(env, ws, side_steps))
-                if world == 1:      # unfused library strawman on the same GPU, same operands
-                    bank_bf16 = torch.empty(w.N, D, dtype=torch.bfloat16, device=device)
-                    for row0, rows in bank_rows_fp32(torch, device, w.bank_seed, 0, w.N):
-                        bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
-                    q_bf16 = torch.nn.functional.normalize(w.q_dev, dim=-1).bfloat16()
-
-                    def straw():
-                        return strawman_topk(torch, q_bf16, bank_bf16, w.k)
-
-                    for _ in range(2):
-                        straw()
-                    st_ms = timer.run(straw, 3, False) / 3
-                    workloads[-1 - len(SMALL_Q)]["strawman_torch_matmul_bf16_topk_ms"] = st_ms
-                    del bank_bf16, q_bf16
-            w.close()
-            del w
-            torch.cuda.empty_cache()
-        if world == 1 and head.name == "synthetic_10m":
-            # strawman on a sample of the headline (the [Q, N] fp32 score block does not fit otherwise)
-            n_q = 1024
-            bank_bf16 = torch.empty(N, D, dtype=torch.bfloat16, device=device)
-            for row0, rows in bank_rows_fp32(torch, device, head.bank_seed, 0, N):
-                bank_bf16[row0:row0 + rows.shape[0]] = torch.nn.functional.normalize(rows, dim=-1).bfloat16()
-            q_bf16 = torch.nn.functional.normalize(head.q_dev[:n_q], dim=-1).bfloat16()
-            strawman_topk(torch, q_bf16, bank_bf16, k)
-            st_ms = timer.run(lambda: strawman_topk(torch, q_bf16, bank_bf16, k), 2, False) / 2
-            ours_ms = timer.run(lambda: bank.search(head.q_dev[:n_q], k), 5, False) / 5
-            workloads.append({"workload": f"{head.name} sample: {n_q} queries vs {N}-row bank, top-{k}",
-                              "ms_per_step": ours_ms, "value": n_q / (ours_ms * 1e-3), "unit": "queries/s",
-                              "strawman_torch_matmul_bf16_topk_ms": st_ms})
-            del bank_bf16, q_bf16
-            torch.cuda.empty_cache()
+        workloads = side_resident(env, head, steps) + workloads_named
 
     cpu_baseline = None
     literal = None
