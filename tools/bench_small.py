@@ -33,16 +33,17 @@ def time_search(rb, q, k, bank_bytes, reps):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps, "back-to-back"
-    ts = []
+    torch.cuda._sleep(4_000_000)        # park the stream: every launch below is queued before the device gets to it
+    pairs = []
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rb.search(q, k)
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return statistics.median(ts), "l2-flushed"
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in pairs), "l2-flushed, parked"
 
 
 SHAPES = [("clotho_eval", 1045, 19195, 5), ("audiocaps", 975, 49838, 10),
