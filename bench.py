@@ -56,6 +56,8 @@ BANK_BLOCK = 65536          # rows per generation block; seed = bank_seed * 2**3
 L2_BYTES = 126 << 20        # B200 L2 capacity
 GATE_SAMPLES = 64
 SHORT_REPS = 50             # repetitions of a side shape whose search takes < 2 ms
+BALANCE_OVERLAP = 0.125     # N > 1: every rank stores this fraction of a shard beyond either end of its own
+BALANCE_EVERY = 2           # ... and the boundaries are re-balanced before every 2nd step
 IDLE_BEFORE_S = 1.0         # pause before a side shape of < 50 ms per search is timed (a power-capped clock recovers)
 GATE_TOL = 1e-3             # north_star: scores within 1e-3 of fp32, index sets equal except near-ties
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -464,7 +466,7 @@ def run_reference(args):
 class Workload:
     """One named shape, bank resident (row-sharded at N > 1), queries resident and pinned."""
 
-    def __init__(self, env, name, Q=None, N=None, k=None, bank=None, label=None):
+    def __init__(self, env, name, Q=None, N=None, k=None, bank=None, label=None, overlap=0.0):
         torch, zs = env["torch"], env["zs"]
         wQ, wN, wk, excl, _, bank_seed = WORKLOADS[name]
         self.env, self.name = env, name
@@ -478,13 +480,19 @@ class Workload:
             self.owns_bank = True
             if world > 1:
                 from zsaac_b200.sharded import ShardedRelatedBank
-                self.bank = ShardedRelatedBank(self.N, D, device=device)
+                self.bank = ShardedRelatedBank(self.N, D, device=device, overlap=overlap)
             else:
                 self.bank = zs.RelatedBank(self.N, D, device=device)
         self.local = self.bank.local if world > 1 else self.bank
-        self.lo, self.hi = (self.bank.lo, self.bank.hi) if world > 1 else (0, self.N)
+        # [lo, hi): this rank's share of the bank in the equal split (what the gate re-scores and
+        # the roofline counts); with overlap the rank STORES more ([store_lo, store_hi)) and the
+        # rows it searches move with the measured speed of the GPUs (sharded.py)
+        self.lo, self.hi = self.bank.base_bounds[env["rank"]] if world > 1 else (0, self.N)
         if self.owns_bank:
-            fill_shard(torch, self.local, self.lo, self.hi, bank_seed, device)
+            s_lo, s_hi = (self.bank.store_lo, self.bank.store_hi) if world > 1 else (0, self.N)
+            for row, rows in bank_rows_fp32(torch, device, bank_seed, s_lo, s_hi):
+                self.local.upload(rows, row - s_lo, normalize=True)
+            torch.cuda.synchronize(device)
         self.q_host, self.q_dev, self.self_index = make_queries(torch, name, self.Q, device)
         self.local.reserve(self.Q, self.k)
         shard_bytes = (self.hi - self.lo) * D * 2 + self.Q * D * 4
@@ -498,6 +506,7 @@ class Workload:
         torch, dist = env["torch"], env["dist"]
         res = self.search()
         torch.cuda.synchronize(env["device"])
+        self.gate_result = res
         g = parity_gate(torch, dist, env["world"], env["device"], self.lo, self.hi, self.bank_seed,
                         self.q_dev, self.self_index, self.k, res)
         if env["world"] > 1:
@@ -666,7 +675,9 @@ def run_ours(args):
     workloads_named = [] if args.headline_only else side_named(env, args.workload, steps)
 
     # ---- headline workload: bank resident in HBM as bf16 before anything is timed
-    head = Workload(env, args.workload, Q=args.queries or None, N=args.bank_rows or None)
+    balance = world > 1 and not args.no_balance
+    head = Workload(env, args.workload, Q=args.queries or None, N=args.bank_rows or None,
+                    overlap=BALANCE_OVERLAP if balance else 0.0)
     Q, N, k = head.Q, head.N, head.k
     local, bank = head.local, head.bank
 
@@ -681,11 +692,13 @@ def run_ours(args):
     # merge -> all-gather -> k-way merge, all on one stream (the fused kernel is persistent and owns
     # every SM: nothing that needs SMs can overlap it, see SearchPipeline), preallocated buffers.
     pipe = SearchPipeline(bank, Q, k, depth=2, from_host=False, to_host=False, result="replicated",
-                          self_index=head.self_index) if world > 1 else None
+                          self_index=head.self_index,
+                          balance_every=BALANCE_EVERY if balance else 0) if world > 1 else None
+    dev_slot = [0]
 
     def step_device():
         if pipe is not None:
-            pipe.submit(head.q_dev)
+            dev_slot[0] = pipe.submit(head.q_dev)
         else:
             head.search()
 
@@ -704,12 +717,24 @@ def run_ours(args):
     launches = local.launch_count - launches0
     ms_per_step = total_ms / steps
     value = Q / (ms_per_step * 1e-3)
+    if pipe is not None:
+        # the shard boundaries have moved since the gate: the result must still be the gated bits
+        ds, di = pipe.result_of(dev_slot[0])
+        flag = torch.tensor([int(torch.equal(ds, head.gate_result[0]) and torch.equal(di, head.gate_result[1]))],
+                            device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gate["timed_result_identical_to_gated"] = bool(flag.item())
+        if not gate["timed_result_identical_to_gated"]:
+            if rank == 0:
+                print(json.dumps({"parity_gate": gate, "error": "result of the timed steps differs from the gated result"}), flush=True)
+            return 3
 
     # ---- timed region 2: host buffers in, host buffers out (e2e).  Every rank uploads the pinned
     # host batch over its own PCIe link and reads back its 1/N of the merged rows; the copy engines
     # run the upload of step i+1 and the read-back of step i-1 under the fused kernel of step i.
     e2e_pipe = SearchPipeline(bank, Q, k, depth=2, from_host=True, to_host=True, result="row_slice",
-                              self_index=head.self_index, input="full")
+                              self_index=head.self_index, input="full",
+                              balance_every=BALANCE_EVERY if balance else 0)
 
     last_slot = [0]
 
@@ -736,9 +761,21 @@ def run_ours(args):
         return 3
     e2e_ms = timer.run(step_e2e, steps, head.flush_l2, finish=e2e_pipe.wait_stream) / steps
     e2e_value = Q / (e2e_ms * 1e-3)
+    hs, hi_ = e2e_pipe.result_of(last_slot[0], host=True)      # (timer.run ended with a device synchronise)
+    flag = torch.tensor([int(torch.equal(hs, ref_s[r_lo:r_hi].cpu()) and torch.equal(hi_, ref_i[r_lo:r_hi].cpu()))],
+                        device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    gate["e2e_timed_readback_identical"] = bool(flag.item())
+    if not gate["e2e_timed_readback_identical"]:
+        if rank == 0:
+            print(json.dumps({"parity_gate": gate, "error": "e2e read-back of the timed steps differs from the device result"}), flush=True)
+        return 3
 
     # ---- roofline of the dominant kernel (this rank's shard) ---------------------------------
     shard_rows = head.hi - head.lo
+    if pipe is not None and pipe.rows_log:      # moving boundaries: the rows this rank searched in the timed steps
+        shard_rows = statistics.mean(pipe.rows_log[-steps:])
     k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
     clock_report = clocks.report()
     capped = ("sw_power_cap" in clock_report["reasons"] and clock_report["sm_mhz"] is not None
@@ -796,7 +833,11 @@ def run_ours(args):
                 "workload": describe(head),
                 "parallelism": (f"bank row-sharded over {world} GPUs, queries replicated, one NCCL all-gather "
                                 "+ k-way merge per step") if world > 1 else "single GPU",
-                "bank_rows_per_gpu": shard_rows,
+                "bank_rows_per_gpu": head.hi - head.lo,
+                "shard_balance": ({"stored_overlap_of_a_shard": BALANCE_OVERLAP, "every_steps": BALANCE_EVERY,
+                                   "rebalances": pipe.rebalances + e2e_pipe.rebalances,
+                                   "rows_per_rank_now": [hi - lo for lo, hi in bank.bounds]}
+                                  if balance else None),
                 "bank_dtype": "bf16", "accumulate": "fp32",
                 "l2": ("L2 flushed between timed steps (256 MB write); bank shard %.0f MB + queries "
                        "%.0f MB per step" % (shard_rows * D * 2 / 1e6, Q * D * 4 / 1e6)) if head.flush_l2
@@ -836,6 +877,8 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override the query count (smoke runs)")
     ap.add_argument("--bank-rows", type=int, default=0, help="override the bank rows (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: fixed equal shards instead of boundaries that follow the measured speed of the GPUs")
     ap.add_argument("--headline-only", action="store_true",
                     help="skip the extra shapes / strawman / literal loop (profiling runs)")
     args = ap.parse_args()

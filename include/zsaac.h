@@ -72,6 +72,15 @@ int zs_bank_alloc(zs_ctx* ctx, int64_t n_rows, int d);
 int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_row,
                    int in_dtype, int normalize, void* stream);
 
+/* Restrict zs_search to bank rows [row_lo, row_lo + n_rows) of the stored bank ("search
+ * window"); returned indices stay global (index_offset + row within the stored bank).  Host-side
+ * only (two tensor maps are re-encoded): cheap enough to call before every search.  Used by the
+ * multi-GPU path, where every rank stores a superset of its shard and the shard boundaries
+ * follow the measured speed of the GPUs (sharded.py); scores do not depend on the window, so
+ * any partition of the bank into windows merges to the same bits.  (0, 0) lifts the window;
+ * zs_bank_alloc lifts it too.  zs_rank_count / zs_debug_scores always see the whole bank. */
+int zs_bank_window(zs_ctx* ctx, int64_t row_lo, int64_t n_rows);
+
 /* out[i, :] = in[i, :] / max(||in[i, :]||_2, 1e-12), fp32 in and out (in-place allowed): the
  * fp32 unit-row bank load_data returns to its caller (reference
  * embeddings_related_generator.py:17).  d must be a multiple of 4.  Needs no bank. */

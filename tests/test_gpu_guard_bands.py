@@ -96,3 +96,45 @@ def test_rescore_gather_merge_stay_inside_their_outputs(zs):
     torch.cuda.synchronize()
     assert torch.equal(ms, ws) and torch.equal(mi, wi)
     rb.close()
+
+
+@pytest.mark.parametrize("solo", ["0", "1"])
+def test_search_window_equals_a_bank_of_those_rows(zs, monkeypatch, solo):
+    """zs_bank_window (the multi-GPU path's movable shard boundaries): searching rows [lo, lo + n)
+    of a stored bank returns the bits a bank holding exactly those rows returns — indices global."""
+    monkeypatch.setenv("ZSAAC_SOLO", solo)
+    N, Q = 20011, 300
+    bank = helpers.seeded((N, 1024), 21, "cuda")
+    bank[9000] = bank[12]                                   # a duplicate inside some windows only
+    q = helpers.seeded((Q, 1024), 22, "cuda")
+    q[0] = bank[12]
+    rb = zs.RelatedBank.from_tensor(bank, index_offset=1000)
+    full = rb.search(q, 10)
+    for lo, n, k in ((0, N, 10), (0, 5000, 10), (4999, 7001, 10), (8999, 2, 2), (12345, N - 12345, 40), (513, 300, 33)):
+        rb.window(lo, n)
+        assert rb.plan(Q, k)[0] >= 1
+        self_index = (torch.arange(Q, device="cuda") % n) + lo + 1000
+        for si in (None, self_index):
+            if si is not None and k > n - 1:
+                continue
+            s, i = rb.search(q, k, self_index=si)
+            part = zs.RelatedBank.from_tensor(bank[lo:lo + n], index_offset=1000 + lo)
+            ws, wi = part.search(q, k, self_index=si)
+            torch.cuda.synchronize()
+            part.close()
+            assert torch.equal(s, ws) and torch.equal(i, wi), (lo, n, k, si is not None)
+            assert (i >= 1000 + lo).all() and (i < 1000 + lo + n).all()
+    with pytest.raises(RuntimeError):
+        rb.window(N - 5, 6)                                 # outside the stored rows
+    rb.window()                                             # lifted: the whole bank again
+    s, i = rb.search(q, 10)
+    torch.cuda.synchronize()
+    assert torch.equal(s, full[0]) and torch.equal(i, full[1])
+    # rank_of / debug_scores always see the whole bank
+    rb.window(100, 1000)
+    ranks, _ = rb.rank_of(q[:5], torch.tensor([12, 9000, 3, 4, 5], device="cuda") + 1000)
+    rb.window()
+    ranks_full, _ = rb.rank_of(q[:5], torch.tensor([12, 9000, 3, 4, 5], device="cuda") + 1000)
+    torch.cuda.synchronize()
+    assert torch.equal(ranks, ranks_full)
+    rb.close()

@@ -23,16 +23,16 @@ def test_sharded_bank_nccl_bit_exact():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
 def test_pipeline_and_generator_sharded_equal_single_gpu(tmp_path):
-    """SearchPipeline (side streams + extra communicators, replicated / row_slice, fp32 re-scoring)
-    and the generator pipeline sharded over the ranks reproduce the single-GPU results bit for bit
-    (embeddings_related_generator.py:19-34 on N GPUs)."""
+    """SearchPipeline (side streams + extra communicators, replicated / row_slice, fp32 re-scoring,
+    adaptive shard boundaries) and the generator pipeline sharded over the ranks reproduce the
+    single-GPU results bit for bit (embeddings_related_generator.py:19-34 on N GPUs)."""
     world = 2 if torch.cuda.device_count() < 4 else (4 if torch.cuda.device_count() < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29518",
            os.path.join(ROOT, "tools", "dist_check_r2.py"), str(tmp_path)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("on all ranks: True") == 12
+    assert out.stdout.count("on all ranks: True") == 15
     assert out.stdout.count("identical to the single-GPU stream: True") == 2
 
 

@@ -28,20 +28,25 @@ class OracleBank:
         self.rows, self.dim, self.index_offset = rows, dim, index_offset
         self.device = torch.device("cpu")
         self.bank = torch.zeros(rows, dim)
+        self.win = (0, rows)
+
+    def window(self, row_lo=0, n_rows=0):
+        self.win = (row_lo, n_rows) if n_rows else (0, self.rows)
 
     def upload(self, rows, dst_row=0, *, normalize=True):
         rows = self.oracle.normalize_rows(rows) if normalize else rows.float()
         self.bank[dst_row:dst_row + rows.shape[0]] = rows
 
     def search(self, queries, k, *, normalize_queries=True, self_index=None, out=None):
+        w_lo, w_n = self.win
         local_self = None
         if self_index is not None:
-            local_self = self_index - self.index_offset
-            local_self = torch.where((local_self >= 0) & (local_self < self.rows), local_self,
+            local_self = self_index - self.index_offset - w_lo
+            local_self = torch.where((local_self >= 0) & (local_self < w_n), local_self,
                                      torch.full_like(local_self, -1))
         q = self.oracle.normalize_rows(queries) if normalize_queries else queries
-        s, i = self.oracle.cosine_topk(q, self.bank, k, normalize=False, self_index=local_self)
-        i = i + self.index_offset
+        s, i = self.oracle.cosine_topk(q, self.bank[w_lo:w_lo + w_n], k, normalize=False, self_index=local_self)
+        i = i + self.index_offset + w_lo
         if out is not None:
             out[0].copy_(s)
             out[1].copy_(i)
@@ -87,6 +92,22 @@ def _worker(rank, world, port, n_rows, k, exclude_self, result_dir):
         sw.upload_global(bank)
         s2, i2 = sw.search(queries, k, self_index=self_index)
         assert torch.equal(i2, wi) and torch.equal(s2, ws)
+        # adaptive boundaries: every rank stores half a shard beyond its own; wherever the
+        # boundary is moved to, the global answer stays the same
+        sa = ShardedRelatedBank(n_rows, 128, local_bank_factory=OracleBank, overlap=0.5)
+        assert sa.adaptive and sa.stores[0][1] > sa.base_bounds[0][1] and sa.stores[1][0] < sa.base_bounds[1][0]
+        sa.upload_global(bank)
+        for cut in (sa.base_bounds[0][1], max(10, sa.stores[1][0]), min(n_rows - 10, sa.stores[0][1]), n_rows // 2 - 7):
+            sa.set_bounds([(0, cut), (cut, n_rows)])
+            s3, i3 = sa.search(queries, k, self_index=self_index)
+            assert torch.equal(i3, wi) and torch.equal(s3, ws), cut
+        with pytest.raises(ValueError, match="stored rows|contiguous"):
+            sa.set_bounds([(0, n_rows), (n_rows, n_rows)])
+        sa.set_bounds(sa.base_bounds)
+        new = sa.rebalance(10.0 if rank == 0 else 12.0)            # rank 1 is slower: it gives rows away
+        assert new == sa.bounds and new[0][1] > sa.base_bounds[0][1]
+        s4, i4 = sa.search(queries, k, self_index=self_index)
+        assert torch.equal(i4, wi) and torch.equal(s4, ws)
         torch.save((s, i), os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -143,3 +164,34 @@ def test_multi_rank_writer_emits_the_single_gpu_stream(tmp_path, world, n_items)
     ranges = [item_range(n_items, r, world) for r in range(world)]
     assert ranges[0][0] == 0 and ranges[-1][1] == n_items
     assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+
+
+def test_rebalanced_bounds_controller():
+    """The boundary controller (sharded.rebalanced_bounds): deterministic, contiguous, inside the
+    stored rows, converging to equal times for constant speeds."""
+    sys.path.insert(0, ROOT)
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200.sharded import rebalanced_bounds, shard_bounds
+    n, world = 10_000_000, 8
+    base = shard_bounds(n, world)
+    margin = 157_184
+    stores = [(max(0, lo - margin), min(n, hi + margin)) for lo, hi in base]
+    ms = [112.2, 109.7, 107.9, 113.4, 109.7, 109.7, 111.5, 107.7]       # measured on 8 B200s of one box
+    speed = [(hi - lo) / t for (lo, hi), t in zip(base, ms)]
+    cur = base
+    for _ in range(6):
+        t = [(hi - lo) / v for (lo, hi), v in zip(cur, speed)]
+        nxt = rebalanced_bounds(cur, t, stores)
+        assert nxt[0][0] == 0 and nxt[-1][1] == n
+        assert all(nxt[r][1] == nxt[r + 1][0] for r in range(world - 1))
+        assert all(stores[r][0] <= lo < hi <= stores[r][1] for r, (lo, hi) in enumerate(nxt))
+        cur = nxt
+    t = [(hi - lo) / v for (lo, hi), v in zip(cur, speed)]
+    assert max(t) - min(t) < 0.2 and max(t) < 110.5                     # from 113.4: the mean is 110.2
+    # equal times: nothing moves (up to the alignment); garbage timings: nothing moves at all
+    assert all(abs(a[1] - b[1]) <= 256 for a, b in zip(rebalanced_bounds(base, [5.0] * world, stores), base))
+    assert rebalanced_bounds(base, [1.0, float("nan")] + [1.0] * 6, stores) == [tuple(b) for b in base]
+    assert rebalanced_bounds(base, [0.0] * world, stores) == [tuple(b) for b in base]
+    # a rank that is 3x slower is clamped at what its neighbours store
+    slow = rebalanced_bounds(base, [3.0] + [1.0] * 7, stores, damping=1.0)
+    assert slow[0][1] == stores[1][0]

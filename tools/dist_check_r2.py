@@ -80,8 +80,52 @@ def main():
                 if rank == 0:
                     print(f"[dist_check_r2] pipeline result={result} from_host={from_host} input={how} rescore={rescore}: "
                           f"bit-exact vs single GPU on all ranks: {good}", flush=True)
-    whole.close()
     sb.local.close()
+
+    # ---------------------------------------------------------------- adaptive shard boundaries
+    # every rank stores 1/4 of a shard beyond its own rows; the pipeline re-balances every 2
+    # batches from measured times, a second bank gets boundaries pushed to the limits by hand
+    sa = ShardedRelatedBank(N, 1024, device=device, overlap=0.25)
+    sa.upload_global(bank)
+    torch.cuda.synchronize()
+    for result in ("replicated", "row_slice"):
+        pipe = SearchPipeline(sa, Q, k, depth=2, from_host=True, to_host=True, result=result, balance_every=2)
+        same, moved = True, False
+        for step in range(9):
+            sl = pipe.submit(q_host)
+            pipe.wait_stream(sl)
+            torch.cuda.synchronize()
+            lo, hi = pipe.out_rows
+            ds, di = pipe.result_of(sl)
+            same &= torch.equal(ds, s1[lo:hi]) and torch.equal(di, i1[lo:hi])
+            moved |= sa.bounds != [tuple(b) for b in sa.base_bounds]
+        same &= pipe.rebalances >= 3
+        good = all_ok(same, device)
+        ok &= good
+        if rank == 0:
+            print(f"[dist_check_r2] adaptive boundaries result={result} ({pipe.rebalances} re-balances, "
+                  f"boundaries moved: {moved}, sizes {[hi - lo for lo, hi in sa.bounds]}): "
+                  f"bit-exact vs single GPU on all ranks: {good}", flush=True)
+    same = True
+    for shift in (-1, +1):                                 # every boundary at its limit, alternating direction
+        cuts = [0]
+        for r in range(1, world):
+            lim = sa.stores[r][0] if (r % 2 == 0) == (shift > 0) else sa.stores[r - 1][1]
+            cuts.append(max(lim, cuts[-1] + 64))
+        cuts.append(N)
+        sa.set_bounds([(cuts[r], cuts[r + 1]) for r in range(world)])
+        for kk in (k, 40):
+            ws, wi = whole.search(queries, kk)
+            s2, i2 = sa.search(queries, kk)
+            torch.cuda.synchronize()
+            same &= torch.equal(s2, ws) and torch.equal(i2, wi)
+    good = all_ok(same, device)
+    ok &= good
+    if rank == 0:
+        print(f"[dist_check_r2] boundaries at the limits of the stored rows, k = {k} and 40: "
+              f"bit-exact vs single GPU on all ranks: {good}", flush=True)
+    whole.close()
+    sa.local.close()
 
     # ---------------------------------------------------------------- generator, sharded vs single GPU
     workdir = sys.argv[1] if len(sys.argv) > 1 else tempfile.gettempdir()

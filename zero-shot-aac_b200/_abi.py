@@ -39,6 +39,7 @@ SIGNATURES = {
     "zs_destroy": (_int, [_c_ctx]),
     "zs_bank_alloc": (_int, [_c_ctx, _i64, _int]),
     "zs_bank_upload": (_int, [_c_ctx, _ptr, _i64, _i64, _int, _int, _ptr]),
+    "zs_bank_window": (_int, [_c_ctx, _i64, _i64]),
     "zs_normalize_rows_f32": (_int, [_c_ctx, _ptr, _ptr, _i64, _int, _ptr]),
     "zs_bank_rows": (_i64, [_c_ctx]),
     "zs_bank_dim": (_int, [_c_ctx]),

@@ -78,6 +78,9 @@ struct zs_ctx {
   int64_t bank_rows = 0;
   int bank_d = 0;
   CUtensorMap bank_map[2];     // [0]: box {64, 256} (cta_group::1)  [1]: box {64, 128} (cta_group::2)
+  // search window (zs_bank_window): zs_search ranks rows [win_lo, win_lo + win_rows) only
+  int64_t win_lo = 0, win_rows = 0;   // win_rows == 0: no window, the whole bank
+  CUtensorMap win_map[2];
 
   __nv_bfloat16* q_ws = nullptr;  // bf16 (normalised) queries
   int64_t q_ws_rows = 0;
@@ -154,6 +157,17 @@ int kcap_for(int k) {
   return k <= 8 ? 8 : (k <= 12 ? 12 : (k <= 16 ? 16 : (k <= 24 ? 24 : 32)));
 }
 
+// rows zs_search ranks: the window if one is set, else the whole bank
+int64_t search_rows(const zs_ctx* ctx) { return ctx->win_rows > 0 ? ctx->win_rows : ctx->bank_rows; }
+
+// zs_rank_count / zs_debug_scores always work on the whole bank: the window is lifted for the call
+struct WholeBank {
+  zs_ctx* ctx;
+  int64_t lo, rows;
+  explicit WholeBank(zs_ctx* c) : ctx(c), lo(c->win_lo), rows(c->win_rows) { c->win_lo = c->win_rows = 0; }
+  ~WholeBank() { ctx->win_lo = lo; ctx->win_rows = rows; }
+};
+
 struct Plan {
   int cg, m_tiles, n_tiles, chunks, tiles_per_chunk, ctas;
   int sync_window, windows_per_unit, max_iters;   // lock-step of the bank stream (0 = off)
@@ -174,7 +188,7 @@ Plan make_plan_for(const zs_ctx* ctx, int64_t Q, int k, int cg) {
   pl.cg = cg;
   const int workers = std::max(1, ctx->sm_count / cg);
   pl.m_tiles = static_cast<int>((Q + zs::BLOCK_M * cg - 1) / (zs::BLOCK_M * cg));
-  pl.n_tiles = static_cast<int>((ctx->bank_rows + zs::BLOCK_N - 1) / zs::BLOCK_N);
+  pl.n_tiles = static_cast<int>((search_rows(ctx) + zs::BLOCK_N - 1) / zs::BLOCK_N);
   const int max_chunks = std::min(pl.n_tiles, zs::MERGE_MAX_LISTS / zs::EPI_HALVES);
   double best_cost = 1e300;
   int best_s = 1;
@@ -539,9 +553,33 @@ int zs_bank_alloc(zs_ctx* ctx, int64_t n_rows, int d) {
     ctx->bank_rows = n_rows;
     ctx->bank_d = d;
   }
+  ctx->win_lo = ctx->win_rows = 0;
   int rc = encode_rows_map(ctx, &ctx->bank_map[0], ctx->bank, n_rows, d, zs::BLOCK_N);
   if (rc) return rc;
   return encode_rows_map(ctx, &ctx->bank_map[1], ctx->bank, n_rows, d, zs::BLOCK_N / 2);
+}
+
+int zs_bank_window(zs_ctx* ctx, int64_t row_lo, int64_t n_rows) {
+  if (!ctx || !ctx->bank) return fail(ZS_ERR_STATE, "zs_bank_window: no bank");
+  if (n_rows == 0 && row_lo == 0) {          // back to the whole bank
+    ctx->win_lo = ctx->win_rows = 0;
+    return ZS_OK;
+  }
+  if (row_lo < 0 || n_rows < 1 || row_lo + n_rows > ctx->bank_rows)
+    return fail(ZS_ERR_INVALID, "zs_bank_window: rows [%lld, %lld) outside the bank of %lld rows",
+                (long long)row_lo, (long long)(row_lo + n_rows), (long long)ctx->bank_rows);
+  DeviceGuard guard(ctx->device);
+  const __nv_bfloat16* base = ctx->bank + row_lo * ctx->bank_d;   // d % 64 == 0: 128-byte aligned rows
+  CUtensorMap maps[2];
+  int rc = encode_rows_map(ctx, &maps[0], base, n_rows, ctx->bank_d, zs::BLOCK_N);
+  if (rc) return rc;
+  rc = encode_rows_map(ctx, &maps[1], base, n_rows, ctx->bank_d, zs::BLOCK_N / 2);
+  if (rc) return rc;
+  ctx->win_map[0] = maps[0];
+  ctx->win_map[1] = maps[1];
+  ctx->win_lo = row_lo;
+  ctx->win_rows = n_rows;
+  return ZS_OK;
 }
 
 int zs_bank_upload(zs_ctx* ctx, const void* rows, int64_t n_rows, int64_t dst_row, int in_dtype,
@@ -689,7 +727,7 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
 
   zs::SimTopkParams p{};
   p.Q = static_cast<int>(Q);
-  p.n_bank = static_cast<int>(ctx->bank_rows);
+  p.n_bank = static_cast<int>(search_rows(ctx));
   p.num_k_blocks = ctx->bank_d / zs::BLOCK_K;
   p.num_m_tiles = pl.m_tiles;
   p.num_n_tiles = pl.n_tiles;
@@ -697,6 +735,11 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
   p.num_chunks = pl.chunks;
   p.k = k_pass;
   p.self_index = reinterpret_cast<const long long*>(self_index);
+  // with a window the kernel sees rows [win_lo, win_lo + win_rows) as columns 0 .. win_rows - 1
+  const bool windowed = ctx->win_rows > 0;
+  index_offset += windowed ? ctx->win_lo : 0;
+  const CUtensorMap* wmap1 = windowed ? &ctx->win_map[0] : nullptr;
+  const CUtensorMap* wmap2 = windowed ? &ctx->win_map[1] : nullptr;
   p.index_offset = index_offset;
   p.part_scores = ctx->part_scores;
   p.part_idx = ctx->part_idx;
@@ -744,8 +787,8 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
     p.out_scores = out_scores;
     p.out_idx = reinterpret_cast<long long*>(out_indices);
     p.out_stride = out_stride;
-    rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
-                      : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+    rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st, wmap2)
+                      : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st, wmap1);
     if (rc == ZS_OK) {
       ctx->solo_state = 1;
       ctx->cnt_base[0] = p.cast_target;
@@ -772,8 +815,8 @@ int search_pass(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k_
   // programmatic dependent launch: cast kernel -> fused kernel -> merge (not while profiling,
   // the timing events would sit between the kernels)
   ctx->pdl_next = cast_queries && ctx->pdl_enabled && !ctx->profiling;
-  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st)
-                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st);
+  rc = (pl.cg == 2) ? dispatch_simtopk<2>(ctx, qmap, p, pl.ctas, false, st, wmap2)
+                    : dispatch_simtopk<1>(ctx, qmap, p, pl.ctas, false, st, wmap1);
   ctx->pdl_next = false;
   if (rc) return rc;
   ZS_CUDA(launch_merge<int>(ctx->part_scores, ctx->part_idx, n_lists, Q * k_pass, Q * k_pass, Q, k_pass,
@@ -794,11 +837,11 @@ int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k, i
   if (Q < 0 || Q > 0x7fffff00ll) return fail(ZS_ERR_INVALID, "zs_search: Q=%lld", (long long)Q);
   if (q_dtype != ZS_F32 && q_dtype != ZS_BF16)
     return fail(ZS_ERR_INVALID, "zs_search: unknown query dtype %d", q_dtype);
-  const int64_t avail = ctx->bank_rows - (self_index ? 1 : 0);
+  const int64_t avail = search_rows(ctx) - (self_index ? 1 : 0);
   if (k < 1 || k > ZS_MAX_K || k > avail)
     return fail(ZS_ERR_INVALID,
                 "zs_search: selected index k out of range (k=%d, bank rows=%lld%s, max k=%d)", k,
-                (long long)ctx->bank_rows, self_index ? " minus the excluded row" : "", ZS_MAX_K);
+                (long long)search_rows(ctx), self_index ? " minus the excluded row" : "", ZS_MAX_K);
   if (Q == 0) return ZS_OK;
   if (!queries || !out_scores || !out_indices)
     return fail(ZS_ERR_INVALID, "zs_search: null queries / output pointer");
@@ -839,6 +882,7 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
   if (!aligned16(queries)) return fail(ZS_ERR_INVALID, "zs_rank_count: queries must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WholeBank whole(ctx);
   int rc = ensure_workspace(ctx, Q, 1);
   if (rc) return rc;
   const Plan pl = make_plan(ctx, Q, 1);
@@ -1290,6 +1334,7 @@ int zs_debug_scores(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, in
     return fail(ZS_ERR_INVALID, "zs_debug_scores: unknown query dtype %d", q_dtype);
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WholeBank whole(ctx);
   int rc = ensure_workspace(ctx, Q, 1);
   if (rc) return rc;
   CUtensorMap qmap;

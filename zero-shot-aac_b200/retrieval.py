@@ -60,6 +60,7 @@ class RelatedBank:
         self.rows = int(rows)
         self.dim = int(dim)
         self.index_offset = int(index_offset)
+        self.window_rows = None             # (row_lo, n_rows) while a search window is set
         handle = ctypes.c_void_p()
         _abi.check(self._lib.zs_create(ctypes.byref(handle), dev.index))
         self._handle = handle
@@ -103,6 +104,12 @@ class RelatedBank:
         rows.record_stream(torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------------ search
+    def window(self, row_lo: int = 0, n_rows: int = 0) -> None:
+        """Restrict search() to stored rows [row_lo, row_lo + n_rows) (indices stay global);
+        window() without arguments lifts it.  Host-side only, no synchronisation."""
+        _abi.check(self._lib.zs_bank_window(self._ctx, int(row_lo), int(n_rows)))
+        self.window_rows = (int(row_lo), int(n_rows)) if n_rows else None
+
     def reserve(self, n_queries: int, k: int) -> None:
         _abi.check(self._lib.zs_reserve(self._ctx, int(n_queries), int(k)))
 

@@ -12,6 +12,13 @@ extension for banks that outgrow one GPU's time budget (BASELINE config 4: 10 M 
 
 Scores of a (query, bank row) pair do not depend on the shard layout (same K-loop order in the
 kernel), so the merged result is bit-identical to the single-GPU result.
+
+Adaptive shard boundaries (overlap > 0, SearchPipeline(balance_every=n)): every step ends in an
+exchange, so the slowest GPU of the box sets the pace, and the GPUs of one box differ by 3-7 %
+under the power cap.  Each rank therefore STORES a superset of its shard (its rows plus `overlap`
+of a shard on either side: 180 GB of HBM make that free), searches only a window of it
+(zs_bank_window), and the windows' boundaries follow the measured time per row of every rank:
+because scores do not depend on the partition, moving a boundary never changes a result bit.
 """
 from __future__ import annotations
 
@@ -51,6 +58,42 @@ def shard_bounds(n_rows: int, world: int, weights: Optional[Sequence[float]] = N
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def rebalanced_bounds(bounds: Sequence[Tuple[int, int]], times_ms: Sequence[float],
+                      stores: Sequence[Tuple[int, int]], *, damping: float = 0.6,
+                      align: int = SHARD_ALIGN, min_rows: int = 1) -> List[Tuple[int, int]]:
+    """New contiguous row ranges after one control step.
+
+    bounds    current [lo, hi) of every rank (contiguous, covering [0, N))
+    times_ms  what every rank took for its current range (same list on every rank)
+    stores    rows [s_lo, s_hi) every rank holds in memory: rank r can only be given rows inside
+    Rank r's speed is rows / ms; the target size is N x its share of the summed speeds, approached
+    by `damping` per step; cuts are rounded to `align` rows and clamped so that every range stays
+    inside its rank's stored rows and keeps at least `min_rows`.  Deterministic: every rank
+    computes the same answer from the same inputs.  Invalid timings leave the bounds unchanged."""
+    world = len(bounds)
+    n_rows = bounds[-1][1]
+    sizes = [hi - lo for lo, hi in bounds]
+    t = [float(x) for x in times_ms]
+    if len(t) != world or any(not (x > 0.0) or x == float("inf") for x in t):
+        return [tuple(b) for b in bounds]
+    speed = [n / x for n, x in zip(sizes, t)]
+    total = sum(speed)
+    target = [n_rows * v / total for v in speed]
+    new = [n + damping * (g - n) for n, g in zip(sizes, target)]
+    cuts, acc = [0], 0.0
+    for r in range(1, world):
+        acc += new[r - 1]
+        cut = int(round(acc / align)) * align
+        # rank r-1 holds rows below stores[r-1][1], rank r rows from stores[r][0] on
+        cut = min(cut, stores[r - 1][1], n_rows - (world - r) * min_rows)
+        cut = max(cut, stores[r][0], cuts[-1] + min_rows)
+        cuts.append(cut)
+    cuts.append(n_rows)
+    out = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    ok = all(hi - lo >= min_rows and lo >= stores[r][0] and hi <= stores[r][1] for r, (lo, hi) in enumerate(out))
+    return out if ok else [tuple(b) for b in bounds]
+
+
 def _default_local_bank(rows: int, dim: int, device, index_offset: int):
     from .retrieval import RelatedBank   # needs CUDA + the native library: no fallback
     return RelatedBank(rows, dim, device=device, index_offset=index_offset)
@@ -66,7 +109,7 @@ class ShardedRelatedBank:
 
     def __init__(self, n_rows: int, dim: int, *, device=None, group=None,
                  local_bank_factory: Optional[Callable] = None,
-                 shard_weights: Optional[Sequence[float]] = None):
+                 shard_weights: Optional[Sequence[float]] = None, overlap: float = 0.0):
         if not dist.is_initialized():
             raise RuntimeError("ShardedRelatedBank needs an initialised torch.distributed process group")
         self.group = group
@@ -77,24 +120,75 @@ class ShardedRelatedBank:
         # shard_weights (identical on every rank): relative speed of the ranks' GPUs.  Every search
         # ends in an all-gather, so the slowest GPU sets the pace; the GPUs of one box differ by
         # several per cent under the power cap, and shards sized by measured speed even that out.
-        self.bounds = shard_bounds(self.n_rows, self.world, shard_weights)
-        self.lo, self.hi = self.bounds[self.rank]
-        if min(hi - lo for lo, hi in self.bounds) < 1:
+        self.base_bounds = shard_bounds(self.n_rows, self.world, shard_weights)
+        if min(hi - lo for lo, hi in self.base_bounds) < 1:
             raise ValueError(f"bank of {n_rows} rows cannot be sharded over {self.world} ranks")
+        # overlap: every rank stores this fraction of a shard beyond either end of its own, so
+        # that set_bounds() can move the boundaries later without moving a byte
+        if not 0.0 <= overlap <= 1.0:
+            raise ValueError(f"overlap must be a fraction of a shard in [0, 1], got {overlap}")
+        per = -(-self.n_rows // self.world)
+        margin = -(-int(overlap * per) // SHARD_ALIGN) * SHARD_ALIGN if overlap > 0 else 0
+        self.stores = [(max(0, lo - margin), min(self.n_rows, hi + margin)) for lo, hi in self.base_bounds]
+        self.store_lo, self.store_hi = self.stores[self.rank]
+        self.bounds = [tuple(b) for b in self.base_bounds]
+        self.lo, self.hi = self.bounds[self.rank]
         factory = local_bank_factory or _default_local_bank
-        self.local = factory(self.hi - self.lo, self.dim, device, self.lo)
+        self.local = factory(self.store_hi - self.store_lo, self.dim, device, self.store_lo)
         self.device = self.local.device
+        self.adaptive = margin > 0
+        self._cpu_group = None
+        if self.adaptive:
+            self.local.window(self.lo - self.store_lo, self.hi - self.lo)
+
+    # ---------------------------------------------------------------- adaptive boundaries
+    def set_bounds(self, bounds: Sequence[Tuple[int, int]]) -> None:
+        """Make [lo_r, hi_r) the rows rank r searches from now on (same list on every rank:
+        contiguous, covering the bank, inside every rank's stored rows).  Host-side only."""
+        bounds = [(int(lo), int(hi)) for lo, hi in bounds]
+        if len(bounds) != self.world or bounds[0][0] != 0 or bounds[-1][1] != self.n_rows or \
+                any(bounds[r][1] != bounds[r + 1][0] for r in range(self.world - 1)):
+            raise ValueError(f"bounds must be {self.world} contiguous ranges covering [0, {self.n_rows})")
+        for r, (lo, hi) in enumerate(bounds):
+            if hi - lo < 1 or lo < self.stores[r][0] or hi > self.stores[r][1]:
+                raise ValueError(f"rank {r}: rows [{lo}, {hi}) are not inside its stored rows "
+                                 f"[{self.stores[r][0]}, {self.stores[r][1]})")
+        self.bounds = bounds
+        self.lo, self.hi = bounds[self.rank]
+        if self.adaptive:
+            self.local.window(self.lo - self.store_lo, self.hi - self.lo)
+
+    def cpu_group(self):
+        """A gloo group over the same ranks: the timings that steer the boundaries are exchanged
+        on the host, beside the GPU work (an NCCL collective would queue behind the running search)."""
+        if self._cpu_group is None:
+            ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
+            self._cpu_group = dist.new_group(ranks=ranks, backend="gloo")
+        return self._cpu_group
+
+    def rebalance(self, my_ms: float, *, damping: float = 0.6) -> List[Tuple[int, int]]:
+        """One control step: exchange what every rank takes for its CURRENT rows (host-side
+        all-gather), move the boundaries towards equal times, apply them.  Collective."""
+        times = [None] * self.world
+        dist.all_gather_object(times, float(my_ms), group=self.cpu_group())
+        small = self.n_rows < 64 * SHARD_ALIGN * self.world           # small banks: exact cuts
+        new = rebalanced_bounds(self.bounds, times, self.stores, damping=damping,
+                                align=1 if small else SHARD_ALIGN,
+                                min_rows=max(1, min(SHARD_ALIGN, min(hi - lo for lo, hi in self.base_bounds) // 4)))
+        self.set_bounds(new)
+        return new
 
     # ---------------------------------------------------------------- bank
     def upload_local(self, rows: torch.Tensor, dst_row: int = 0, *, normalize: bool = True) -> None:
-        """Store `rows` at LOCAL rows [dst_row, dst_row + n) of this rank's shard."""
+        """Store `rows` at LOCAL rows [dst_row, dst_row + n) of this rank's STORED rows
+        [store_lo, store_hi) (= its shard [lo, hi) unless the bank was built with overlap)."""
         self.local.upload(rows, dst_row, normalize=normalize)
 
     def upload_global(self, bank: torch.Tensor, *, normalize: bool = True) -> None:
         """Every rank passes the same full [N, d] bank; each keeps its own row range."""
         if bank.shape[0] != self.n_rows:
             raise ValueError(f"bank has {bank.shape[0]} rows, expected {self.n_rows}")
-        self.local.upload(bank[self.lo:self.hi], 0, normalize=normalize)
+        self.local.upload(bank[self.store_lo:self.store_hi], 0, normalize=normalize)
 
     # ---------------------------------------------------------------- queries
     def replicate_from_host(self, host_queries: torch.Tensor) -> torch.Tensor:
@@ -182,6 +276,12 @@ class SearchPipeline:
     shard, re-scores them in fp32 (zs_rescore_f32) and passes its k best ON: shard lists carry
     fp32 scores, so the merged result is the fp32 ranking (reference
     embeddings_related_generator.py:22) wherever the true top-k lies inside the candidate sets.
+
+    balance_every = n > 0 (sharded bank built with overlap > 0): before every n-th batch the ranks
+    exchange (on the host, over gloo, while the previous batch is still running on the GPUs) what
+    their shard-local search took over the last n finished batches, and the shard boundaries move
+    towards equal times (ShardedRelatedBank.rebalance).  The result does not depend on the
+    boundaries; the slowest GPU of the box stops setting the pace of every batch.
     """
 
     def __init__(self, bank, n_queries: int, k: int, *, depth: int = 2, from_host: bool = True,
@@ -189,7 +289,8 @@ class SearchPipeline:
                  self_index: Optional[torch.Tensor] = None, normalize_queries: bool = True,
                  query_dtype: torch.dtype = torch.float32,
                  rescore_from: Optional[torch.Tensor] = None, rescore_margin: int = 8,
-                 excludes_self: bool = False, input: str = "full"):
+                 excludes_self: bool = False, input: str = "full", balance_every: int = 0,
+                 balance_damping: float = 0.6):
         if result not in ("replicated", "row_slice"):
             raise ValueError(f"result must be 'replicated' or 'row_slice', got {result!r}")
         if input not in ("full", "replicate", "slice"):
@@ -247,6 +348,14 @@ class SearchPipeline:
             self.slots.append(slot)
         self.local.reserve(self.q, self.kc)
         self._next = 0
+        self.balance_every = int(balance_every) if (self.sharded and G > 1 and getattr(bank, "adaptive", False)) else 0
+        self.balance_damping = float(balance_damping)
+        if rescore_from is not None and self.balance_every:
+            raise ValueError("balance_every and rescore_from cannot be combined (rescore_from is sized to the shard)")
+        self._step = 0
+        self._timed = []          # (step, start event, end event, rows) of the shard-local searches
+        self.rebalances = 0
+        self.rows_log = []        # bank rows this rank searched, per submitted batch
         up_rows = q if input == "full" else (self.hi - self.lo)
         self.h2d_bytes = up_rows * self.dim * torch.empty((), dtype=query_dtype).element_size() if from_host else 0
         self.d2h_bytes = rows_out * self.k * 12 if to_host else 0
@@ -267,6 +376,8 @@ class SearchPipeline:
             self_index = self.self_index
         if self_index is not None:
             self_index = self_index.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        if self.balance_every and self._step >= self.balance_every + 1 and self._step % self.balance_every == 0:
+            self._rebalance()
         idx = self._next
         self._next = (self._next + 1) % len(self.slots)
         slot = self.slots[idx]
@@ -301,9 +412,15 @@ class SearchPipeline:
                 mine = q_full[self.rank * self.per:(self.rank + 1) * self.per]
                 dist.all_gather_into_tensor(q_full.view(-1), mine.reshape(-1), group=self.group)
             if self.rescore_from is None:
+                if self.balance_every:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record(self.s_main)
                 self.local.search(q_dev, self.k, normalize_queries=self.normalize_queries,
                                   self_index=self_index,
                                   out=(slot["local_s"][:self.q], slot["local_i"][:self.q]))
+                if self.balance_every:
+                    ev1.record(self.s_main)
+                    self._timed.append((self._step, ev0, ev1, self.bank.hi - self.bank.lo))
             else:
                 self.local.search(q_dev, self.kc, normalize_queries=self.normalize_queries,
                                   self_index=self_index, out=(slot["cand_s"], slot["cand_i"]))
@@ -333,7 +450,24 @@ class SearchPipeline:
             slot["out_done"].record(self.s_main)
         slot["keepalive"] = (queries, self_index)     # inputs of kernels still queued on the side streams
         slot["used"] = True
+        self._step += 1
+        self.rows_log.append((self.bank.hi - self.bank.lo) if self.sharded else self.local.rows)
         return idx
+
+    def _rebalance(self) -> None:
+        """Called before batch n is enqueued (n a multiple of balance_every): batches up to n - 2
+        have finished or are about to — waiting for the end of batch n - 2 keeps the host at most
+        two batches ahead of the GPU and costs the GPU nothing, batch n - 1 is queued behind it."""
+        done = [t for t in self._timed if t[0] <= self._step - 2]
+        use = done[-self.balance_every:]
+        if not use:
+            return
+        use[-1][2].synchronize()
+        # time per row, so that batches searched under older boundaries still count
+        ms_per_row = sum(a.elapsed_time(b) / rows for _, a, b, rows in use) / len(use)
+        self._timed = [t for t in self._timed if t[0] > use[-1][0]]
+        self.bank.rebalance(ms_per_row * (self.bank.hi - self.bank.lo), damping=self.balance_damping)
+        self.rebalances += 1
 
     def wait_stream(self, idx: Optional[int] = None) -> None:
         """Make the current stream wait for slot `idx` (all slots if None) — no host sync."""
