@@ -788,6 +788,18 @@ def run_ours(args):
         dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
         roofline["kernel_ms_per_rank"] = [round(v, 3) for v in per_rank.tolist()]
         roofline["step_tail_ms_beyond_slowest_kernel"] = round(ms_per_step - max(per_rank.tolist()), 3)
+        # ... of THAT step: the mean over steps of the slowest rank's kernel exceeds the slowest
+        # rank's mean when the step-to-step noise of the GPUs is of the order of their differences
+        n_k = min(len(kernel_ms), steps)
+        per_step = torch.zeros(world, max(n_k, 1), device=device)
+        if n_k:
+            per_step[rank, :n_k] = torch.tensor(kernel_ms[-n_k:], device=device)
+        dist.all_reduce(per_step, op=dist.ReduceOp.SUM)
+        slowest = per_step.max(dim=0).values
+        roofline["slowest_kernel_per_step_ms"] = {"mean": round(slowest.mean().item(), 3),
+                                                  "min": round(slowest.min().item(), 3),
+                                                  "max": round(slowest.max().item(), 3),
+                                                  "std_of_a_rank": round(per_step.std(dim=1).mean().item(), 3)}
     roofline["kernel_share_of_step"] = k_ms / ms_per_step
     roofline["traffic"] = None
     try:
