@@ -137,6 +137,7 @@ class ShardedRelatedBank:
         self.local = factory(self.store_hi - self.store_lo, self.dim, device, self.store_lo)
         self.device = self.local.device
         self.adaptive = margin > 0
+        self.mpr_sum, self.mpr_n = 0.0, 0      # running mean of this rank's milliseconds per bank row
         self._cpu_group = None
         if self.adaptive:
             self.local.window(self.lo - self.store_lo, self.hi - self.lo)
@@ -278,9 +279,9 @@ class SearchPipeline:
     embeddings_related_generator.py:22) wherever the true top-k lies inside the candidate sets.
 
     balance_every = n > 0 (sharded bank built with overlap > 0): before every n-th batch the ranks
-    exchange (on the host, over gloo, while the previous batch is still running on the GPUs) what
-    their shard-local search took over the last n finished batches, and the shard boundaries move
-    towards equal times (ShardedRelatedBank.rebalance).  The result does not depend on the
+    exchange (on the host, over gloo, while the previous batch is still running on the GPUs) their
+    running mean time per bank row, and the shard boundaries move to where those predict equal
+    times (ShardedRelatedBank.rebalance).  The result does not depend on the
     boundaries; the slowest GPU of the box stops setting the pace of every batch.
     """
 
@@ -290,7 +291,7 @@ class SearchPipeline:
                  query_dtype: torch.dtype = torch.float32,
                  rescore_from: Optional[torch.Tensor] = None, rescore_margin: int = 8,
                  excludes_self: bool = False, input: str = "full", balance_every: int = 0,
-                 balance_damping: float = 0.6):
+                 balance_damping: float = 1.0):
         if result not in ("replicated", "row_slice"):
             raise ValueError(f"result must be 'replicated' or 'row_slice', got {result!r}")
         if input not in ("full", "replicate", "slice"):
@@ -457,16 +458,23 @@ class SearchPipeline:
     def _rebalance(self) -> None:
         """Called before batch n is enqueued (n a multiple of balance_every): batches up to n - 2
         have finished or are about to — waiting for the end of batch n - 2 keeps the host at most
-        two batches ahead of the GPU and costs the GPU nothing, batch n - 1 is queued behind it."""
-        done = [t for t in self._timed if t[0] <= self._step - 2]
-        use = done[-self.balance_every:]
-        if not use:
+        two batches ahead of the GPU and costs the GPU nothing, batch n - 1 is queued behind it.
+
+        What steers the boundaries is each rank's time PER ROW averaged over every batch finished
+        so far (the first one excepted): under the power cap the step-to-step noise of one GPU
+        (sigma ~ 2 % of a 110 ms kernel) is as large as the differences between the GPUs of a box,
+        so a controller that follows the last few batches only adds its own jitter; the running
+        mean gets better by 1 / sqrt(n) and the boundaries settle."""
+        done = [t for t in self._timed if 1 <= t[0] <= self._step - 2]
+        if not done:
             return
-        use[-1][2].synchronize()
-        # time per row, so that batches searched under older boundaries still count
-        ms_per_row = sum(a.elapsed_time(b) / rows for _, a, b, rows in use) / len(use)
-        self._timed = [t for t in self._timed if t[0] > use[-1][0]]
-        self.bank.rebalance(ms_per_row * (self.bank.hi - self.bank.lo), damping=self.balance_damping)
+        done[-1][2].synchronize()
+        for _, a, b, rows in done:           # (kept on the bank: every pipeline over it adds to the same mean)
+            self.bank.mpr_sum += a.elapsed_time(b) / rows
+            self.bank.mpr_n += 1
+        self._timed = [t for t in self._timed if t[0] > done[-1][0]]
+        mean_ms = self.bank.mpr_sum / self.bank.mpr_n * (self.bank.hi - self.bank.lo)
+        self.bank.rebalance(mean_ms, damping=self.balance_damping)
         self.rebalances += 1
 
     def wait_stream(self, idx: Optional[int] = None) -> None:
