@@ -157,6 +157,88 @@ def test_parallel_writer_emits_the_same_bytes_as_the_serial_loop(tmp_path, monke
     assert not list(tmp_path.glob("*.part*"))
 
 
+def test_default_writer_emits_the_bytes_of_pickle_dump(tmp_path, monkeypatch):
+    """The default writer fills torch's per-storage stream into a template instead of running
+    torch.save per tensor; the file must hold exactly the bytes of the reference's loop
+    (`pickle.dump(item, file)` per record, embeddings_related_generator.py:30-34) for every kind of
+    value a record may carry — and whatever is not a plain CPU tensor must take torch's own
+    reduction (also byte for byte)."""
+    import io
+    import pickle
+    from zsaac_b200 import related_pipeline as rp
+    g = torch.Generator().manual_seed(12)
+    base = torch.randn(6, 8, generator=g)
+    shared = torch.randn(1, 64, generator=g)                       # one audio embedding, many records
+    attr = torch.randn(3, generator=g)
+    attr.note = "python state"                                     # -> _rebuild_from_type_v2
+    conj = torch.randn(2, generator=g, dtype=torch.complex64).conj()
+    items = [{"audio_embedding": shared, "caption": f"caption {i}", "audio_id": f"Y{i:05d}.wav",
+              "text_embedding": torch.randn(1, 64, generator=g),
+              "related_embeddings": torch.randn(5, 64, generator=g),
+              "view": base[:, ::2], "row": base[3], "tail": base[2:, 4:], "t": base.t(),
+              "long": torch.arange(7) * i, "int32": torch.arange(3, dtype=torch.int32),
+              "int16": torch.arange(3, dtype=torch.int16), "int8": torch.arange(3, dtype=torch.int8),
+              "uint8": torch.arange(300).to(torch.uint8), "bool": torch.tensor([True, False, True]),
+              "half": torch.randn(3, generator=g).half(), "bf16": torch.randn(70000, generator=g).bfloat16(),
+              "f64": torch.randn(2, 2, generator=g, dtype=torch.float64),
+              "empty": torch.empty(0), "empty2d": torch.empty(0, 64), "scalar": torch.tensor(2.5),
+              "twice": [shared, shared, base, base[1]],              # memoised object / shared storage
+              "nested": {"k": (torch.ones(2), [torch.zeros(1, dtype=torch.int64)])},
+              "leaf": torch.randn(3, generator=g).requires_grad_(),  # autograd state
+              "param": torch.nn.Parameter(torch.randn(2, generator=g)),   # subclass
+              "attr": attr, "conj": conj, "complex": torch.randn(2, generator=g, dtype=torch.complex64),
+              "fp8": torch.randn(4, generator=g).to(torch.float8_e4m3fn),  # newer storage format
+              "placeholder": 0, "none": None, "float": 1.5, "bytes": b"\x00\x01", "big": 2 ** 70}
+             for i in range(30)]
+    want = io.BytesIO()
+    for item in items:
+        pickle.dump(item, want)                                    # reference :34
+    path = tmp_path / "out.pkl"
+    rp.save_data_to_hdf5(iter(items), str(path), len(items))
+    assert path.read_bytes() == want.getvalue()
+    # the template path was really taken (and only for plain tensors)
+    calls = {"n": 0}
+    real = torch.storage.TypedStorage.__reduce__
+
+    def counting(self):
+        calls["n"] += 1
+        return real(self)
+
+    monkeypatch.setattr(torch.storage.TypedStorage, "__reduce__", counting)
+    plain_only = [{"caption": "c", "text_embedding": torch.randn(1, 64, generator=g),
+                   "related_embeddings": torch.randn(5, 64, generator=g)} for _ in range(20)]
+    sink = io.BytesIO()
+    for item in plain_only:
+        rp._dump_record(item, sink, False)
+    assert calls["n"] == 0                                         # templates known: torch.save never ran
+    monkeypatch.undo()
+    ref = io.BytesIO()
+    for item in plain_only:
+        pickle.dump(item, ref)
+    assert sink.getvalue() == ref.getvalue()
+    # large records (> one 64 KiB pickle frame, the bytes object written outside the frames)
+    big = {"caption": "big", "related_embeddings": torch.randn(100, 1024, generator=g),
+           "text_embedding": torch.randn(1, 1024, generator=g)}
+    a, b = io.BytesIO(), io.BytesIO()
+    rp._dump_record(big, a, False)
+    pickle.dump(big, b)
+    assert a.getvalue() == b.getvalue()
+    # a template that does not reproduce torch's bytes is dropped, not used
+    monkeypatch.setattr(rp, "_STORAGE_TEMPLATES", {})
+    monkeypatch.setattr(rp, "_storage_template", lambda dtype, numel: (b"not", b"torch's", b"bytes"))
+    a, b = io.BytesIO(), io.BytesIO()
+    rp._dump_record(plain_only[0], a, False)
+    pickle.dump(plain_only[0], b)
+    assert a.getvalue() == b.getvalue() and set(rp._STORAGE_TEMPLATES.values()) == {False}
+    monkeypatch.undo()
+    # the switch restores the literal loop
+    monkeypatch.setenv("ZSAAC_TEMPLATE_PICKLE", "0")
+    monkeypatch.setattr(rp, "_template_dump", None)                # would raise if called
+    off = tmp_path / "off.pkl"
+    rp.save_data_to_hdf5(iter(items), str(off), len(items))
+    assert off.read_bytes() == want.getvalue()
+
+
 def test_fast_pickle_stream_loads_to_the_same_records(tmp_path, monkeypatch):
     """save_data_to_hdf5(fast_pickle=True): different bytes, but the reference's reader loop
     (dataset/dataset.py:64-78, restated in helpers.read_related_stream) gets the same dicts of
@@ -254,6 +336,101 @@ def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
     calls["slow"] = 0
     again = rp._read_records([str(a)])
     assert calls["slow"] > 0 and torch.equal(again[3]["view"], want[3]["view"])
+
+
+def test_read_templates_only_match_streams_they_reproduce():
+    """The reader skips unpickling for a storage stream that equals an already parsed one except
+    for the storage key and the data; anything else must fall through to the full parser."""
+    import io
+    import pickle
+    from zsaac_b200 import related_pipeline as rp
+
+    class Payloads(pickle.Unpickler):                 # the bytes handed to torch.storage._load_from_bytes
+        def find_class(self, module, name):
+            if (module, name) == ("torch.storage", "_load_from_bytes"):
+                return lambda b: b
+            if (module, name) == ("torch._utils", "_rebuild_tensor_v2"):
+                return lambda *a: a[0]
+            return super().find_class(module, name)
+
+    def payload_of(t):
+        return Payloads(io.BytesIO(pickle.dumps(t))).load()
+
+    g = torch.Generator().manual_seed(5)
+    rp._READ_TEMPLATES.clear()
+    a, b = torch.randn(3, 8, generator=g), torch.randn(3, 8, generator=g)
+    pa, pb = payload_of(a), payload_of(b)
+    assert rp._match_read_template(pa) is None                          # nothing known yet
+    assert torch.equal(rp._storage_from_legacy_bytes(pa).flat, a.reshape(-1))
+    assert len(rp._READ_TEMPLATES) == 1
+    assert torch.equal(rp._match_read_template(pb), b.reshape(-1))      # other key, other data
+    flat = rp._match_read_template(pb)
+    flat[0] = 1.0                                                       # owns writable memory
+    assert rp._match_read_template(pb)[0] == b.reshape(-1)[0]
+    # same layout, other element count / dtype: not this template
+    assert rp._match_read_template(payload_of(torch.randn(25, generator=g))) is None
+    assert rp._match_read_template(payload_of(torch.arange(24, dtype=torch.int32))) is None
+    # damaged streams: truncated, longer, keys that differ, a count that differs, non-digit key
+    head = rp._READ_TEMPLATES[0][0]
+    p = len(head)
+    klen = int.from_bytes(pb[p + 1:p + 5], "little")
+    assert rp._match_read_template(pb[:-1]) is None and rp._match_read_template(pb + b"\0") is None
+    second = pb.index(pb[p:p + 5 + klen], p + 5 + klen)
+    swapped = bytearray(pb)
+    swapped[second + 5] = ord("9") if swapped[second + 5] != ord("9") else ord("8")
+    assert rp._match_read_template(bytes(swapped)) is None
+    letters = pb.replace(pb[p + 5:p + 5 + klen], b"k" * klen)
+    assert rp._match_read_template(letters) is None
+    count_at = len(pb) - 24 * 4 - 8
+    wrong = bytearray(pb)
+    wrong[count_at] ^= 1
+    assert rp._match_read_template(bytes(wrong)) is None
+    # zero-element storages and the most-recently-used order
+    e = torch.empty(0)
+    assert rp._storage_from_legacy_bytes(payload_of(e)).flat.numel() == 0
+    assert rp._match_read_template(payload_of(torch.empty(0))).numel() == 0
+    assert rp._READ_TEMPLATES[0][4] == 0
+    assert torch.equal(rp._match_read_template(pa), a.reshape(-1)) and rp._READ_TEMPLATES[0][4] == 24
+    for n in range(1, 40):                                              # the list stays bounded
+        rp._storage_from_legacy_bytes(payload_of(torch.zeros(n)))
+    assert len(rp._READ_TEMPLATES) == rp._READ_TEMPLATES_MAX
+
+
+def test_record_reader_matches_the_reference_loop(tmp_path):
+    """dataset.read_related_records = the reader loops of dataset/dataset.py:64-78 (8-20-word
+    captions kept, list objects spliced) and :401-417 (everything kept), on a stream written by the
+    generator's writer with a list object appended, as the reference's datasets accept."""
+    import pickle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from zsaac_b200 import related_pipeline as rp
+    from zsaac_b200.dataset import read_related_records
+    g = torch.Generator().manual_seed(21)
+    words = "a dog barks far away while cars pass by on the wet road and a door slams shut twice then silence falls".split()
+    items = [{"caption": " ".join(words[:3 + i % 21]), "audio_id": f"Y{i}.wav",
+              "text_embedding": torch.randn(1, 64, generator=g),
+              "related_embeddings": torch.randn(5, 64, generator=g)} for i in range(60)]
+    a, b = tmp_path / "a.pkl", tmp_path / "b.pkl"
+    rp.save_data_to_hdf5(iter(items[:40]), str(a), 40)
+    rp.save_data_to_hdf5(iter(items[40:]), str(b), 20, fast_pickle=True)
+    extra = [{"caption": "short one", "text_embedding": torch.randn(1, 64, generator=g)} for _ in range(3)]
+    with open(a, "ab") as f:
+        pickle.dump(extra, f)                                    # a list object: spliced, never filtered
+    want_all = helpers.read_related_stream(str(a)) + helpers.read_related_stream(str(b))
+    got_all = read_related_records([str(a), str(b)])
+    assert len(got_all) == len(want_all) == 63
+    want_filtered = [it for it in want_all[:40] if 8 <= len(it["caption"].split()) <= 20] + want_all[40:43] \
+        + [it for it in want_all[43:] if 8 <= len(it["caption"].split()) <= 20]
+    got_filtered = read_related_records([str(a), str(b)], caption_words=(8, 20))
+    assert 3 < len(got_filtered) == len(want_filtered) < 63
+    for got, want in ((got_all, want_all), (got_filtered, want_filtered)):
+        for x, y in zip(got, want):
+            assert x.keys() == y.keys() and x["caption"] == y["caption"]
+            for key in x:
+                if isinstance(y[key], torch.Tensor):
+                    assert type(x[key]) is torch.Tensor and x[key].dtype == y[key].dtype
+                    assert x[key].shape == y[key].shape and torch.equal(x[key], y[key])
+    assert len(read_related_records(str(b))) == 20               # one path instead of a list
 
 
 def _plan_dry(sm, n, q, k, cg=0):

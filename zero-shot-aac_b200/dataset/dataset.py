@@ -67,3 +67,36 @@ def collate_with_sound_effects(batch, *, sound_effect_embeddings: torch.Tensor,
     if training:
         return tokens, mask, prefix, padding_hard_prompt, hard_prompts_masks
     return audio_id, prefix, padding_hard_prompt, hard_prompts_masks
+
+
+def read_related_records(data_path, caption_words=None) -> list:
+    """The record reader of the reference's datasets, for the stream the generator scripts write.
+
+    Reference: dataset/dataset.py:64-78 (ClapDataset: `pickle.load` until EOFError, a list object
+    is spliced in, a dict is appended if its caption has 8-20 words -> caption_words=(8, 20)) and
+    :401-417 (the hard-prompt datasets: every dict is kept -> caption_words=None).  `data_path`
+    is a list of files like the reference's, or one path.  Same records as the reference's loop;
+    the tensors inside are rebuilt by the direct parser of torch's per-tensor storage stream that
+    load_data uses (related_pipeline._FastTensorUnpickler: ~3x faster than `pickle.load`, which
+    runs a full torch.load per tensor; anything unusual goes through torch's own loader).  Host
+    only — needs neither CUDA nor the native library."""
+    import pickle
+    from ..related_pipeline import _FastTensorUnpickler
+    paths = [data_path] if isinstance(data_path, (str, bytes)) else list(data_path)
+    all_data: list = []
+    for dp in paths:
+        with open(dp, "rb") as f:
+            while True:
+                try:
+                    item = _FastTensorUnpickler(f).load()
+                except EOFError:
+                    break
+                if type(item) is list:
+                    all_data.extend(item)
+                elif caption_words is None:
+                    all_data.append(item)
+                else:
+                    n_words = len(item["caption"].split())
+                    if caption_words[0] <= n_words <= caption_words[1]:
+                        all_data.append(item)
+    return all_data

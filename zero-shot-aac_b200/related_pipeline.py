@@ -55,11 +55,59 @@ class _PersistentIdUnpickler(pickle.Unpickler):
         return pid
 
 
+# Streams already parsed once, as (head, middle, tail, dtype, element count, element size): what
+# precedes, separates and follows the two occurrences of the storage key.  A stream that matches
+# one of them byte for byte needs no unpickling at all — only the key and the data differ between
+# the tensors of a file.  Most recently matched first; a handful of entries (one per dtype and
+# element count seen).
+_READ_TEMPLATES: list = []
+_READ_TEMPLATES_MAX = 16
+
+
+def _match_read_template(b: bytes):
+    """The flat tensor of a stream that matches a known template, else None."""
+    for slot, (head, middle, tail, dtype, count, size) in enumerate(_READ_TEMPLATES):
+        if not b.startswith(head):
+            continue
+        p = len(head)
+        if len(b) < p + 5 or b[p] != 0x58:                         # BINUNICODE: 'X' + uint32 length
+            continue
+        field_end = p + 5 + int.from_bytes(b[p + 1:p + 5], "little")
+        field = b[p:field_end]
+        if not field[5:].isdigit():
+            continue
+        q = field_end + len(middle)
+        r = q + len(field) + len(tail)
+        if (len(b) != r + 8 + count * size or b[field_end:q] != middle or b[q:q + len(field)] != field
+                or b[q + len(field):r] != tail or int.from_bytes(b[r:r + 8], "little") != count):
+            continue
+        if slot:
+            _READ_TEMPLATES.insert(0, _READ_TEMPLATES.pop(slot))
+        if count == 0:
+            return torch.empty(0, dtype=dtype)
+        return torch.frombuffer(bytearray(memoryview(b)[r + 8:]), dtype=dtype)
+    return None
+
+
+def _remember_read_template(b: bytes, key: str, pos: int, dtype, count: int, size: int) -> None:
+    import struct
+    if not isinstance(key, str) or not key.isdigit():
+        return
+    ident = key.encode()
+    parts = b[:pos].split(b"X" + struct.pack("<I", len(ident)) + ident)
+    if len(parts) == 3:
+        _READ_TEMPLATES.insert(0, (parts[0], parts[1], parts[2], dtype, count, size))
+        del _READ_TEMPLATES[_READ_TEMPLATES_MAX:]
+
+
 def _storage_from_legacy_bytes(b: bytes):
     import io
     import struct
     slow = torch.storage._load_from_bytes
     try:
+        flat = _match_read_template(b)
+        if flat is not None:
+            return _FlatStorage(flat)
         f = io.BytesIO(b)
         if pickle.load(f) != _LEGACY_MAGIC or pickle.load(f) != _LEGACY_PROTOCOL:
             return slow(b)
@@ -82,6 +130,7 @@ def _storage_from_legacy_bytes(b: bytes):
             flat = torch.empty(0, dtype=dtype)
         else:
             flat = torch.frombuffer(bytearray(memoryview(b)[pos + 8:]), dtype=dtype)
+        _remember_read_template(b, pid[2], pos, dtype, count, size)
         return _FlatStorage(flat)
     except Exception:
         return slow(b)
@@ -361,9 +410,107 @@ class _FastTensorPickler(pickle.Pickler):
         return NotImplemented
 
 
+# ------------------------------------------------------------------------------------------------
+# The default writer.  `pickle.dump(item, file)` (reference :34) spends ~100 us per tensor inside
+# torch's reduction: Tensor.__reduce_ex__ wraps the storage in a TypedStorage whose __reduce__ runs
+# a complete legacy torch.save (three header pickles, a persistent-id pickler, a key list) into a
+# BytesIO, and the resulting bytes are what the record pickle embeds.  For a plain CPU tensor that
+# byte string is a fixed template around two things: the storage key (str(storage._cdata), twice)
+# and the raw data.  The reducer below takes the template ONCE per (dtype, element count) from
+# torch.save itself — so it follows whatever the installed torch writes — and then fills it in:
+# the bytes on disk are the very bytes `pickle.dump` writes (tests/test_host_cpu.py compares the
+# streams), ~5x faster.  Everything that is not a plain tensor (subclasses, autograd state, Python
+# attributes, names, conj/neg bits, other devices or layouts, dtypes of the newer storage format)
+# goes through torch's own reduction, and a template that does not reproduce torch's bytes for the
+# first tensor it is used on is dropped.  ZSAAC_TEMPLATE_PICKLE=0 restores the literal
+# `pickle.dump`.
+_TEMPLATE_DTYPES = frozenset(_STORAGE_DTYPES.values())
+_STORAGE_TEMPLATES: dict = {}       # (dtype, element count) -> (head, middle, tail) | False
+
+
+class _LegacyStorageBytes:
+    """Pickles as `torch.storage._load_from_bytes(payload)`, like torch's TypedStorage.__reduce__."""
+    __slots__ = ("payload",)
+
+    def __init__(self, payload: bytes):
+        self.payload = payload
+
+
+def _reduce_storage_bytes(stub: _LegacyStorageBytes):
+    return (torch.storage._load_from_bytes, (stub.payload,))
+
+
+def _key_field(cdata: int) -> bytes:
+    import struct
+    ident = str(cdata).encode()
+    return b"X" + struct.pack("<I", len(ident)) + ident          # BINUNICODE, as protocol 2 writes it
+
+
+def _storage_template(dtype: torch.dtype, numel: int):
+    """Split what torch.save(storage) writes for a CPU storage of this dtype and element count
+    around the two occurrences of the storage key; False if the stream does not have that shape."""
+    import io
+    probe = torch.empty(numel, dtype=dtype)._typed_storage()
+    buf = io.BytesIO()
+    torch.save(probe, buf, _use_new_zipfile_serialization=False)
+    raw = buf.getvalue()
+    nbytes = numel * torch._utils._element_size(dtype)
+    parts = raw[:len(raw) - nbytes].split(_key_field(probe._cdata))
+    return tuple(parts) if len(parts) == 3 else False
+
+
+def _reduce_plain_tensor(t: torch.Tensor):
+    """dispatch_table entry for exactly torch.Tensor: the tuple Tensor.__reduce_ex__ returns, with
+    the storage bytes filled into the template instead of produced by a torch.save call."""
+    import collections
+    import ctypes
+    if (t.device.type == "cpu" and t.layout is torch.strided and t.dtype in _TEMPLATE_DTYPES
+            and not t.requires_grad and not t.has_names() and not torch._utils._get_obj_state(t)
+            and not torch._utils.get_tensor_metadata(t)
+            and not torch.serialization._serialization_tls.skip_data):
+        storage = t.untyped_storage()
+        nbytes = storage.nbytes()
+        numel = nbytes // t.element_size()
+        key = (t.dtype, numel)
+        template = _STORAGE_TEMPLATES.get(key)
+        first_use = template is None
+        if first_use:
+            template = _storage_template(t.dtype, numel) if numel * t.element_size() == nbytes else False
+        if template:
+            field = _key_field(storage._cdata)
+            payload = b"".join((template[0], field, template[1], field, template[2],
+                                ctypes.string_at(storage.data_ptr(), nbytes) if nbytes else b""))
+            if first_use and payload != t._typed_storage().__reduce__()[1][0]:
+                template = False                                   # not torch's bytes: never used
+        if first_use:
+            _STORAGE_TEMPLATES[key] = template
+        if template:
+            return (torch._utils._rebuild_tensor_v2,
+                    (_LegacyStorageBytes(payload), t.storage_offset(), tuple(t.size()), t.stride(),
+                     False, collections.OrderedDict()))
+    return t.__reduce_ex__(pickle.DEFAULT_PROTOCOL)
+
+
+def _template_dump(item, file) -> None:
+    import copyreg
+    pickler = pickle.Pickler(file)
+    table = dict(copyreg.dispatch_table)
+    table[torch.Tensor] = _reduce_plain_tensor
+    table[_LegacyStorageBytes] = _reduce_storage_bytes
+    pickler.dispatch_table = table
+    pickler.dump(item)
+
+
+def _template_pickle_enabled() -> bool:
+    import os
+    return os.environ.get("ZSAAC_TEMPLATE_PICKLE", "1") != "0"
+
+
 def _dump_record(item: dict, file, fast: bool) -> None:
     if fast:
         _FastTensorPickler(file, protocol=pickle.DEFAULT_PROTOCOL).dump(item)
+    elif _template_pickle_enabled():
+        _template_dump(item, file)                       # the bytes of reference :34, faster
     else:
         pickle.dump(item, file)                          # reference :34
 
