@@ -375,15 +375,44 @@ def strawman_topk(torch, q_bf16, bank_bf16, k, q_chunk=1024, n_chunk=1_000_000):
     return torch.cat(out_s), torch.cat(out_i)
 
 
+def workload_config(name: str, Q: int, N: int, k: int, excl: bool, world: int, balance: bool = False) -> dict:
+    """`config` of the JSON line: what is measured, as a function of the command line only, so that
+    both arms (ours, --impl reference) of the same command print the SAME dict.  Everything that
+    depends on the run (launch plan, achieved TFLOP/s, moved shard boundaries) is under `details`."""
+    rows_per_gpu = shard_rows_of(N, world)
+    shard_bytes = rows_per_gpu * D * 2 + Q * D * 4
+    if shard_bytes < 2 * L2_BYTES:
+        l2 = ("L2 flushed between timed steps (256 MB write); bank shard %.0f MB + queries %.0f MB per step"
+              % (rows_per_gpu * D * 2 / 1e6, Q * D * 4 / 1e6))
+    else:
+        l2 = ("inputs larger than L2: bank shard %.1f GB + queries %.0f MB per step"
+              % (rows_per_gpu * D * 2 / 1e9, Q * D * 4 / 1e6))
+    return {
+        "workload": f"{name}: {Q} queries vs {N}-row bank, d={D}, top-{k}" + (", self-exclusion" if excl else ""),
+        "parallelism": (f"bank row-sharded over {world} GPUs, queries replicated, one NCCL all-gather "
+                        "+ k-way merge per step") if world > 1 else "single GPU",
+        "bank_rows_per_gpu": rows_per_gpu,
+        "shard_balance": ({"stored_overlap_of_a_shard": BALANCE_OVERLAP, "every_steps": BALANCE_EVERY}
+                          if (balance and world > 1) else None),
+        "bank_dtype": "bf16", "accumulate": "fp32", "l2": l2,
+    }
+
+
+def shard_rows_of(N: int, world: int) -> int:
+    """Rows of the largest shard of the equal split (sharded.shard_bounds: ceil(N / world) each)."""
+    return -(-N // world)
+
+
 class CpuReference:
     """The reference's CPU formulation on a bounded sample of the workload (built once, timed
     per pass).  The sample is a slice of the same synthetic data; queries/s is scaled linearly in
     the bank rows left out (the cost per query is linear in N)."""
 
-    def __init__(self, torch, name: str):
+    def __init__(self, torch, name: str, Q: int = 0, N: int = 0):
         from oracle import oracle
         self.torch, self.oracle, self.name = torch, oracle, name
-        Q, N, k, _, q_seed, bank_seed = WORKLOADS[name]
+        wQ, wN, k, _, q_seed, bank_seed = WORKLOADS[name]
+        Q, N = Q or wQ, N or wN                                     # (--queries / --bank-rows overrides)
         self.N, self.k = N, k
         self.n_s = min(N, 1_000_000)
         self.q_s = min(Q, 1024)          # ~0.5 s (400 k rows) to ~1.7 s (1 M rows) of 16-thread work per pass
@@ -437,7 +466,8 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)
     name = args.workload
     Q, N, k, excl, _, _ = WORKLOADS[name]
-    ref = CpuReference(torch, name)
+    Q, N = args.queries or Q, args.bank_rows or N
+    ref = CpuReference(torch, name, Q, N)
     times = []
     for step in range(args.warmup + args.steps):
         dt = ref.one_pass()
@@ -452,9 +482,12 @@ def run_reference(args):
         "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {Q} queries vs {N}-row bank, d={D}, top-{k}"
-                               + (", self-exclusion" if excl else ""),
-                   "device": "host CPU", "sample_queries": q_s, "sample_bank_rows": n_s},
+        # the same `config` our arm prints for this command line (the workload both arms measure);
+        # what this arm actually ran — a bounded sample of it on the host — is in `reference_sample`
+        "config": workload_config(name, Q, N, k, excl, max(1, args.gpus), args.balance),
+        "reference_sample": {"device": "host CPU", "threads": cb["cores"], "sample_queries": q_s,
+                             "sample_bank_rows": n_s,
+                             "scaled_to_bank_rows": N if n_s != N else None},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -817,7 +850,7 @@ def run_ours(args):
     literal = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        ref = CpuReference(torch, head.name)
+        ref = CpuReference(torch, head.name, Q, N)
         cpu_baseline = ref.baseline(min(ref.one_pass() for _ in range(3)))
         if not args.headline_only:
             # the reference's literal loop on config 1: CPU port, and on this GPU as written
@@ -841,20 +874,14 @@ def run_ours(args):
             "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": describe(head),
-                "parallelism": (f"bank row-sharded over {world} GPUs, queries replicated, one NCCL all-gather "
-                                "+ k-way merge per step") if world > 1 else "single GPU",
-                "bank_rows_per_gpu": head.hi - head.lo,
-                "shard_balance": ({"stored_overlap_of_a_shard": BALANCE_OVERLAP, "every_steps": BALANCE_EVERY,
-                                   "rebalances": pipe.rebalances + e2e_pipe.rebalances,
+            "config": workload_config(head.name, Q, N, k, head.excl, world, balance),
+            "details": {
+                "bank_rows_this_rank": head.hi - head.lo,
+                "bank_rows_searched_per_step_this_rank": shard_rows,
+                "shard_balance": ({"rebalances": pipe.rebalances + e2e_pipe.rebalances,
                                    "rows_per_rank_now": [hi - lo for lo, hi in bank.bounds]}
                                   if balance else None),
-                "bank_dtype": "bf16", "accumulate": "fp32",
-                "l2": ("L2 flushed between timed steps (256 MB write); bank shard %.0f MB + queries "
-                       "%.0f MB per step" % (shard_rows * D * 2 / 1e6, Q * D * 4 / 1e6)) if head.flush_l2
-                      else ("inputs larger than L2: bank shard %.1f GB + queries %.0f MB per step"
-                            % (shard_rows * D * 2 / 1e9, Q * D * 4 / 1e6)),
+                "l2_flushed_between_steps": bool(head.flush_l2),
                 "plan_chunks_tiles_ctas": list(plan),
                 "tflops": 2.0 * Q * N * D / (ms_per_step * 1e-3) / 1e12,
             },

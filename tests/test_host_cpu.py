@@ -338,6 +338,42 @@ def test_fast_unpickler_returns_the_same_records(tmp_path, monkeypatch):
     assert calls["slow"] > 0 and torch.equal(again[3]["view"], want[3]["view"])
 
 
+def test_bench_reference_arm_prints_our_config(tmp_path):
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line with
+    the contract's keys, the SAME `config` dict our arm prints for that command line, rank 0 alone
+    under a multi-rank launch."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--workload", "clotho_eval", "--queries", "64", "--bank-rows", "4096"]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["config"] == bench.workload_config("clotho_eval", 64, 4096, 5, False, 1)
+    assert line["config"]["workload"].startswith("clotho_eval: 64 queries vs 4096-row bank")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
+    # N = 4 command line: same shard arithmetic as sharded.shard_bounds, config names the sharding
+    cfg4 = bench.workload_config("synthetic_10m", 65536, 10_000_000, 32, False, 4)
+    assert cfg4["bank_rows_per_gpu"] == shard_bounds(10_000_000, 4)[0][1] == 2_500_000
+    assert "4 GPUs" in cfg4["parallelism"] and cfg4["l2"].startswith("inputs larger than L2")
+    assert bench.workload_config("clotho_eval", 1045, 19195, 5, False, 1)["l2"].startswith("L2 flushed")
+    # every rank but 0 of a multi-rank launch exits 0 without printing
+    env.update(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
 def test_read_templates_only_match_streams_they_reproduce():
     """The reader skips unpickling for a storage stream that equals an already parsed one except
     for the storage key and the data; anything else must fall through to the full parser."""

@@ -46,7 +46,7 @@ if [[ "$ARGS" == *" restream "* ]]; then
     python - <<PY
 import json
 d = json.loads(open("gpurun_out/ab_restream_chunks$CH.json").read().strip().splitlines()[-1])
-print(json.dumps({"chunks": $CH, "plan": d["config"]["plan_chunks_tiles_ctas"], "ms_per_step": d["ms_per_step"],
+print(json.dumps({"chunks": $CH, "plan": d["details"]["plan_chunks_tiles_ctas"], "ms_per_step": d["ms_per_step"],
                   "kernel_ms": d["roofline"]["kernel_ms"], "sm_mhz": d["clocks"]["sm_mhz"]}))
 PY
   done
