@@ -112,8 +112,11 @@ int zs_reserve(zs_ctx* ctx, int64_t Q, int k);
  * Deterministic: the result is the exact top-k of the bf16 scores under (score desc, index asc)
  * whatever the launch geometry or timing (the work units exchange admission thresholds while
  * they run, which changes only how much each unit contributes, never the merged result).
- * Three kernels are enqueued on `stream` (cast, fused similarity/top-k, merge); the context's
- * workspaces are in use until they finish, so searches on one context must not overlap. */
+ * One kernel (129 ... 4,096 queries: cast and merge run inside the fused kernel) or three (cast,
+ * fused similarity/top-k, merge) are enqueued on `stream` per pass of 32; the context's
+ * workspaces are in use until they finish, so searches on one context must not overlap.
+ * Returns ZS_ERR_KERNEL (and enqueues nothing) once a kernel of this context has reported a
+ * pipeline time-out (zs_kernel_error). */
 int zs_search(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int k,
               int normalize_queries, const int64_t* self_index, int64_t index_offset,
               float* out_scores, int64_t* out_indices, void* stream);
@@ -136,7 +139,8 @@ int zs_rank_count(zs_ctx* ctx, const void* queries, int64_t Q, int q_dtype, int 
  * predict_prompt.py:23-29: sim = q @ B.T; p = softmax(100 * sim); out = p @ B; out /= ||out||).
  *   queries [Q, d] fp32, bank [n_rows, d] fp32 (the caller's text_features tensor, read in place:
  *   no bank upload needed), out [Q, d] fp32.  d a multiple of 4, <= 1024.  One streaming pass
- *   over the bank per group of 2 queries (the reference calls it with one audio embedding). */
+ *   over the bank per query on banks of 256 MB or more, per pair of queries on smaller ones (the
+ *   reference calls it with one audio embedding); batches go to zs_memory_project_batched. */
 int zs_memory_project(zs_ctx* ctx, const float* queries, int64_t Q, const float* bank, int64_t n_rows,
                       int d, float temperature, float* out, void* stream);
 
@@ -199,7 +203,7 @@ int zs_merge(zs_ctx* ctx, const float* scores, const int64_t* indices, int S, in
  * dot product otherwise — and the k best under (score desc, index asc) are returned.
  *   queries     [Q, d] fp32 (raw: normalisation happens here), bank [n_rows, d] fp32
  *   candidates  [Q, kc] int64 global indices (index_offset = global index of bank row 0;
- *               entries < 0 or outside the bank are ignored), kc <= 32
+ *               entries < 0 or outside the bank are ignored), k <= kc <= 2048
  *   out_scores  [Q, k] fp32, out_indices [Q, k] int64 (-1 where fewer than k candidates exist)
  * Stand-alone: needs no bf16 bank. */
 int zs_rescore_f32(zs_ctx* ctx, const float* queries, int64_t Q, int normalize, const float* bank,
