@@ -79,6 +79,9 @@ CASES = {
                           duplicates=[(150, 3), (151, 3), (152, 90)], module="single"),
     "wavcaps_k70_clustered": dict(seed=1006, n=300, k=70, dist="clustered", centres=6, sigma=0.05,
                                   files=[100, 200], module="wavcaps"),
+    # a bank of several bank tiles and a query batch of several query tiles (single-launch mode of
+    # the fused kernel), --topnumber 10 as in BASELINE config 2
+    "generator_n2048_k10": dict(seed=1007, n=2048, k=10, dist="gauss", files=[2048], module="single"),
 }
 
 
