@@ -8,7 +8,6 @@ reduction instead of a top-k, so it lives on the same library (zs_memory_project
 """
 from __future__ import annotations
 
-import pickle
 from typing import List, Sequence
 
 import torch
@@ -95,19 +94,10 @@ def construct_support_memory(text_json: Sequence[str]) -> torch.Tensor:
     embeddings are concatenated and divided by their norms (:54-55; no epsilon — a zero row
     would be NaN there, it stays zero here)."""
     _require_cuda()
-    all_data: List[dict] = list()
-    for dp in text_json:
-        with open(dp, "rb") as f:
-            while True:
-                try:
-                    item = pickle.load(f)
-                    if type(item) is list:
-                        all_data = all_data + item
-                    else:
-                        if len(item["caption"].split()) >= 8 and len(item["caption"].split()) <= 20:
-                            all_data.append(item)
-                except EOFError:
-                    break
+    # the reader loop of :33-47, over the direct parser of torch's per-tensor storage stream
+    # (same records as pickle.load, ~4x faster: dataset.read_related_records)
+    from .dataset.dataset import read_related_records
+    all_data: List[dict] = read_related_records(list(text_json), caption_words=(8, 20))
     rows = [item["text_embedding"].detach().cpu().reshape(1, -1) for item in all_data]
     host = torch.cat(rows, dim=0).to(torch.float32).contiguous().pin_memory()
     dev = host.to("cuda", non_blocking=True)
