@@ -516,3 +516,10 @@ def test_planner_invariants_and_baseline_plans(monkeypatch):
     assert _plan_dry(148, 400_000, 8_192, 10)[0] == 4
     with pytest.raises(RuntimeError):
         _plan_dry(148, 0, 10, 5)
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every C symbol of include/zsaac.h to the reference lines it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_functions() if n not in doc and n.rsplit("_", 1)[0] + "_*" not in doc]
+    assert not missing, missing
