@@ -294,6 +294,35 @@ def test_collate_with_sound_effects_matches_per_sample_reference(zs):
     assert len(ev) == 4 and ev[0] == tuple(f"id{n}" for n in range(5)) and torch.equal(ev[2], w[:5][:, :ev[2].shape[1]])
 
 
+def test_sound_effect_embeddings_choice_matches_the_model_method(zs):
+    """models/caption_model.py:15-21 (the method clap_to_gpt calls in every forward pass): the
+    chosen label embeddings, `bank[index].squeeze(1)`, on the bank's device."""
+    from zsaac_b200.utils import sound_effect_choice, sound_effect_embeddings_choice
+    bank = torch.nn.functional.normalize(helpers.seeded((527, 1024), 51), dim=-1)
+    prefixes = torch.nn.functional.normalize(helpers.seeded((32, 1, 1024), 52), dim=-1)
+
+    def reference(prefix, k):                                            # the method's body, on the CPU
+        return bank[oracle.sound_effect_choice(prefix, bank, k)].squeeze(1)
+
+    bank_gpu = bank.cuda()
+    for prefix, k in ((prefixes, 3), (prefixes[:, 0], 3), (prefixes[:, 0], 1), (prefixes[:5], 1)):
+        want = reference(prefix, k)
+        got = sound_effect_embeddings_choice(prefix.cuda(), bank_gpu, k)
+        assert got.is_cuda and got.dtype == torch.float32 and got.shape == want.shape
+        assert torch.equal(got.cpu(), want)
+        # the same rows the index-returning mirror names
+        idx = sound_effect_choice(prefix, bank, k)
+        assert torch.equal(got.cpu(), bank[idx].squeeze(1))
+    # a CPU bank is ranked on the GPU, the rows come back on the bank's device
+    got = sound_effect_embeddings_choice(prefixes[:4], bank, 3)
+    assert got.device.type == "cpu" and torch.equal(got, reference(prefixes[:4], 3))
+    # autograd as in the reference: into the label embeddings (if they are trained), not the prefix
+    param = torch.nn.Parameter(bank_gpu.clone())
+    out = sound_effect_embeddings_choice(prefixes[:2].cuda().requires_grad_(), param, 3)
+    out.sum().backward()
+    assert param.grad is not None and int((param.grad.abs().sum(dim=1) > 0).sum()) >= 3
+
+
 # ------------------------------------------------------------------------------------- bank cache
 def test_bank_cache_eviction_never_frees_a_bank_in_use(zs):
     """an evicted RelatedBank may still be held by a suspended process_data generator."""

@@ -66,6 +66,9 @@ def test_fails_loudly_without_cuda(tmp_path):
     from zsaac_b200.utils import sound_effect_choice
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sound_effect_choice(q, b, 3)
+    from zsaac_b200.utils import sound_effect_embeddings_choice
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sound_effect_embeddings_choice(q, b, 3)
     from zsaac_b200.data_handing import embeddings_related_generator as gen
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gen.load_data(str(tmp_path / "missing.pkl"))
