@@ -526,3 +526,29 @@ def test_integration_doc_names_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [n for n in declared_functions() if n not in doc and n.rsplit("_", 1)[0] + "_*" not in doc]
     assert not missing, missing
+
+
+def test_bench_roofline_arithmetic():
+    """bench.roofline_of: algorithmic FLOP = 2 Q N d and bytes = 2 N d + 2 Q d + 12 Q k (DESIGN §4.1,
+    SURVEY §8d) over the kernel time, against the measured peaks — the numbers of the round-1
+    driver record (1.3422 PFLOP / 878.97 ms = 1527 TFLOP/s = 1.115 of 1370)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    peaks, src = bench.load_peaks()
+    assert src in ("measured", "fallback") and peaks["bf16_tflops"] >= peaks["bf16_tflops_sustained"] > 0 and peaks["hbm_gbs"] > 0
+    r = bench.roofline_of(peaks, src, 65536, 10_000_000, 32, 878.97, long_step=True)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["kernel"] == "zs_simtopk_kernel"
+    assert abs(r["achieved"] - 2 * 65536 * 1e7 * 1024 / 0.87897 / 1e12) < 1e-6
+    assert abs(r["achieved"] - 1527.0) < 0.5 and r["peak"] == peaks["bf16_tflops_sustained"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["frac_of_burst"] - r["achieved"] / peaks["bf16_tflops"]) < 1e-12
+    burst = bench.roofline_of(peaks, src, 65536, 10_000_000, 32, 878.97, long_step=False)
+    assert burst["peak"] == peaks["bf16_tflops"]
+    # one query against 400 k rows is a bank stream: HBM-bound, bytes / time against the copy bandwidth
+    h = bench.roofline_of(peaks, src, 1, 400_000, 10, 0.131, long_step=False)
+    want = (2.0 * 400_000 * 1024 + 1 * 1024 * 2.0 + 1 * 10 * 12.0) / 0.131e-3 / 1e9
+    assert h["bound"] == "hbm" and h["unit"] == "GB/s" and abs(h["achieved"] - want) < 1e-6
+    assert h["peak"] == peaks["hbm_gbs"] and abs(h["frac"] - want / peaks["hbm_gbs"]) < 1e-12
+    # the ridge: compute-bound from a few hundred queries on (BASELINE.md section 2: ~252 flop/byte)
+    assert bench.roofline_of(peaks, src, 128, 400_000, 10, 0.15, False)["bound"] == "hbm"
+    assert bench.roofline_of(peaks, src, 512, 400_000, 10, 0.31, False)["bound"] == "tensor"
