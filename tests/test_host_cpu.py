@@ -552,3 +552,60 @@ def test_bench_roofline_arithmetic():
     # the ridge: compute-bound from a few hundred queries on (~252 flop/byte)
     assert bench.roofline_of(peaks, src, 128, 400_000, 10, 0.15, False)["bound"] == "hbm"
     assert bench.roofline_of(peaks, src, 512, 400_000, 10, 0.31, False)["bound"] == "tensor"
+
+
+def test_bench_parity_gate_flags_wrong_results():
+    """bench.parity_gate is what stands between a wrong kernel and a published number: it must
+    pass the exact top-k of bf16-rounded operands (what the kernel ranks) and flag every kind of
+    wrong answer — a loser returned, a clear winner missing, scores off, order broken, self kept."""
+    sys.path.insert(0, ROOT)
+    import bench
+    dev = torch.device("cpu")
+    n_rows, n_q, k, seed = 3000, 40, 5, 777
+    _, rows = next(bench.bank_rows_fp32(torch, dev, seed, 0, n_rows))
+    assert tuple(rows.shape) == (n_rows, bench.D)
+    bank_n = torch.nn.functional.normalize(rows, dim=-1)
+    # two shards regenerate the same rows (per-block seeds): what makes the gate world-size independent
+    _, tail = next(bench.bank_rows_fp32(torch, dev, seed, 1000, n_rows))
+    assert torch.equal(tail, rows[1000:])
+
+    def kernel_like(q, self_index=None):
+        s = torch.nn.functional.normalize(q, dim=-1).bfloat16().float() @ bank_n.bfloat16().float().T
+        if self_index is not None:
+            s[torch.arange(q.shape[0]), self_index] = float("-inf")
+        top = torch.sort(s, dim=1, descending=True, stable=True)
+        return top.values[:, :k].contiguous(), top.indices[:, :k].contiguous()
+
+    def gate(q, res, self_index=None):
+        return bench.parity_gate(torch, None, 1, dev, 0, n_rows, seed, q, self_index, k, res)
+
+    q = bench.gen_queries(torch, n_q, 11)
+    s, i = kernel_like(q)
+    g = gate(q, (s, i))
+    assert g["ok"] and g["sampled_queries"] == n_q and g["max_abs_score_err_vs_fp32"] < 3e-4
+    assert g["returned_below_band"] == 0 and g["clear_winners_missing"] == 0 and g["sorted"]
+    assert g["index_agreement_with_fp32"] > 0.9
+    # a loser in the last slot: returned below the band (and the true k-th may be a missing winner)
+    worst = (torch.nn.functional.normalize(q, dim=-1) @ bank_n.T).argmin(dim=1)
+    bad_i = i.clone()
+    bad_i[:, k - 1] = worst
+    g = gate(q, (s, bad_i))
+    assert not g["ok"] and g["returned_below_band"] >= n_q
+    # the best row replaced by a duplicate of the second: a clear winner is missing
+    bad_i = i.clone()
+    bad_i[:, 0] = i[:, 1]
+    g = gate(q, (s, bad_i))
+    assert not g["ok"] and g["clear_winners_missing"] > 0
+    # scores off by more than north_star's 1e-3
+    g = gate(q, (s + 5e-3, i))
+    assert not g["ok"] and g["max_abs_score_err_vs_fp32"] > 4e-3
+    # order broken
+    g = gate(q, (s.flip(1).contiguous(), i.flip(1).contiguous()))
+    assert not g["ok"] and not g["sorted"]
+    # self-exclusion (BASELINE config 5): queries are bank rows; keeping the row itself is flagged
+    q_self = rows[:n_q].clone()
+    me = torch.arange(n_q)
+    g = gate(q_self, kernel_like(q_self, me), me)
+    assert g["ok"] and g["self_excluded"]
+    g = gate(q_self, kernel_like(q_self), me)
+    assert not g["ok"] and not g["self_excluded"]

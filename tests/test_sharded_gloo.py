@@ -195,3 +195,41 @@ def test_rebalanced_bounds_controller():
     # a rank that is 3x slower is clamped at what its neighbours store
     slow = rebalanced_bounds(base, [3.0] + [1.0] * 7, stores, damping=1.0)
     assert slow[0][1] == stores[1][0]
+
+
+def _gate_worker(rank, world, port, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        import zsaac_b200  # noqa: F401
+        from zsaac_b200.sharded import shard_bounds
+        dev = torch.device("cpu")
+        n_rows, n_q, k, seed = 2500, 24, 6, 991
+        _, rows = next(bench.bank_rows_fp32(torch, dev, seed, 0, n_rows))
+        bank_n = torch.nn.functional.normalize(rows, dim=-1)
+        q = bench.gen_queries(torch, n_q, 13)
+        s = torch.nn.functional.normalize(q, dim=-1).bfloat16().float() @ bank_n.bfloat16().float().T
+        top = torch.sort(s, dim=1, descending=True, stable=True)
+        res = (top.values[:, :k].contiguous(), top.indices[:, :k].contiguous())
+        lo, hi = shard_bounds(n_rows, world)[rank]
+        g = bench.parity_gate(torch, dist, world, dev, lo, hi, seed, q, None, k, res)
+        assert g["ok"] and g["sampled_queries"] == n_q, g
+        bad = res[1].clone()
+        bad[:, 0] = res[1][:, 1]
+        g_bad = bench.parity_gate(torch, dist, world, dev, lo, hi, seed, q, None, k, (res[0], bad))
+        assert not g_bad["ok"] and g_bad["clear_winners_missing"] > 0
+        torch.save(g, os.path.join(result_dir, f"gate{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_parity_gate_is_shard_independent_gloo(tmp_path):
+    """bench.parity_gate at N > 1: every rank re-scores ITS shard in fp32, the shard-local fp32
+    top-k lists are all-gathered and merged — every rank reaches the verdict one GPU would."""
+    world = 3
+    mp.spawn(_gate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    gates = [torch.load(tmp_path / f"gate{r}.pt") for r in range(world)]
+    assert all(g == gates[0] for g in gates)
