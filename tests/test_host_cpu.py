@@ -609,3 +609,23 @@ def test_bench_parity_gate_flags_wrong_results():
     assert g["ok"] and g["self_excluded"]
     g = gate(q_self, kernel_like(q_self), me)
     assert not g["ok"] and not g["self_excluded"]
+
+
+def test_c_abi_from_a_c_program(tmp_path):
+    """include/zsaac.h is plain C99 and the library links from a C program (tests/c/abi_smoke.c):
+    version, dry planner, error codes + messages, and zs_create's loud failure without a GPU."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib_dir = os.path.dirname(_abi.library_path())
+    exe = str(tmp_path / "abi_smoke")
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                            "-o", exe, "-L", lib_dir, "-lzsaac_b200", f"-Wl,-rpath,{lib_dir}"],
+                           capture_output=True, text=True, timeout=300)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "plan chunks=13 " in run.stdout and "cta_group=2" in run.stdout     # BASELINE config 4's plan
+    if not torch.cuda.is_available():
+        assert "no CPU path" in run.stdout
