@@ -629,3 +629,45 @@ def test_c_abi_from_a_c_program(tmp_path):
     assert "plan chunks=13 " in run.stdout and "cta_group=2" in run.stdout     # BASELINE config 4's plan
     if not torch.cuda.is_available():
         assert "no CPU path" in run.stdout
+
+
+def test_bench_our_arm_on_standins():
+    """Every line of bench.py's measurement protocol and JSON assembly for OUR arm, executed on the
+    CPU with stand-ins for the CUDA pieces (tests/bench_standins.py): one JSON line carrying every
+    key of the contract, a green parity gate on the stand-in's bf16 emulation, all named shapes, and
+    the same `config` the reference arm prints for that command line."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_standins.py"), "--steps", "3"],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["unit"] == "queries/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 3 and line["dtype"] == "bf16"
+    assert line["value"] > 0 and line["gpu_launches"] > 0
+    assert line["config"] == bench.workload_config("synthetic_10m", 300, 6000, 32, False, 1)
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_share_of_step"):
+        assert key in line["roofline"], key
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 300 * 1024 * 4 and line["e2e"]["d2h_bytes_per_step"] == 300 * 32 * 12
+    assert set(line["clocks"]) == {"sm_mhz", "sm_max_mhz", "reasons"}
+    gate = line["parity_gate"]
+    assert gate["ok"] and gate["e2e_readback_identical"] and gate["e2e_timed_readback_identical"]
+    named = [w["workload"].split(":")[0] for w in line["workloads"]]
+    for name in ("clotho_eval", "audiocaps", "wavcaps_400k", "allpairs_400k", "wavcaps_400k_q1", "wavcaps_400k_q32",
+                 "wavcaps_400k_q128", "synthetic_10m_q1", "synthetic_10m_q32", "synthetic_10m_q128"):
+        assert name in named, (name, named)
+    for w in line["workloads"]:
+        if "parity_gate" in w:
+            assert w["parity_gate"]["ok"] and "roofline" in w and w["launches_per_search"] > 0
+    assert any("strawman_torch_matmul_bf16_topk_ms" in w for w in line["workloads"])
+    lit = line["literal_reference_loop_clotho_eval"]
+    assert lit["cpu"]["value"] > 0 and lit["torch_cuda_as_written"]["value"] > 0
