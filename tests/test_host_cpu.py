@@ -671,3 +671,42 @@ def test_bench_our_arm_on_standins():
     assert any("strawman_torch_matmul_bf16_topk_ms" in w for w in line["workloads"])
     lit = line["literal_reference_loop_clotho_eval"]
     assert lit["cpu"]["value"] > 0 and lit["torch_cuda_as_written"]["value"] > 0
+
+
+@pytest.mark.parametrize("world,balance", [(2, False), (3, True)])
+def test_bench_sharded_protocol_on_standins(world, balance):
+    """bench.py at N > 1 as torchrun drives it, on the CPU: N ranks over gloo, the real
+    ShardedRelatedBank and SearchPipeline around the stand-in bank.  The run must gate itself green
+    (same bits on all ranks and as one "GPU", timed result = gated result, e2e read-back = device
+    result) with fixed and with moving shard boundaries, and rank 0 alone prints the line."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "bench_standins.py"), "--steps", "4", "--world", str(world)]
+    out = subprocess.run(cmd + (["--balance"] if balance else []), capture_output=True, text=True, timeout=1200, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == world and line["scaling"] == "strong" and line["cpu_baseline"] is None
+    assert line["config"] == bench.workload_config("synthetic_10m", 300, 6000, 32, False, world, balance)
+    assert line["config"]["bank_rows_per_gpu"] == 6000 // world
+    gate = line["parity_gate"]
+    assert gate["ok"] and gate["ranks"] == {"identical_on_all_ranks": True, "single_gpu_slice_queries": 300,
+                                            "bit_identical_to_single_gpu": True, "ok": True}
+    assert gate["timed_result_identical_to_gated"] and gate["e2e_readback_identical"]
+    assert gate["e2e_timed_readback_identical"]
+    roof = line["roofline"]
+    assert len(roof["kernel_ms_per_rank"]) == world and roof["traffic"] is None
+    assert set(roof["slowest_kernel_per_step_ms"]) == {"mean", "min", "max", "std_of_a_rank"}
+    # every rank reads back only its slice of the merged rows
+    assert line["e2e"]["d2h_bytes_per_step"] == -(-300 // world) * 32 * 12 * world
+    assert line["e2e"]["h2d_bytes_per_step"] == 300 * 1024 * 4 * world
+    if balance:
+        moved = line["details"]["shard_balance"]
+        assert moved["rebalances"] >= 1 and sum(moved["rows_per_rank_now"]) == 6000
+    else:
+        assert line["details"]["shard_balance"] is None
+    for w in line["workloads"]:
+        assert w["parity_gate"]["ok"] and w["parity_gate"]["ranks"]["identical_on_all_ranks"]

@@ -202,6 +202,6 @@ def _worker(rank, world, port, n_rows, n_q, k):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_rows,n_q,k", [(2, 301, 37, 6), (3, 200, 10, 4), (4, 257, 9, 3), (4, 1000, 64, 10)])
+@pytest.mark.parametrize("world,n_rows,n_q,k", [(3, 200, 10, 4), (4, 257, 9, 3), (4, 1000, 64, 10)])
 def test_search_pipeline_layouts_gloo(world, n_rows, n_q, k):
     mp.spawn(_worker, args=(world, _free_port(), n_rows, n_q, k), nprocs=world, join=True)
