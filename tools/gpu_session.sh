@@ -27,6 +27,8 @@ if [[ "$ARGS" == *" bench "* ]]; then
   echo "bench_small exit $?"; cut -c1-220 gpurun_out/bench_small.jsonl
   timeout 600 python tools/bench_memproj.py > gpurun_out/bench_map2memory.jsonl 2> gpurun_out/bench_map2memory.err
   echo "bench_memproj exit $?"; cut -c1-260 gpurun_out/bench_map2memory.jsonl
+  timeout 300 python tools/bench_writer.py > gpurun_out/writer_box_host_bench.json 2> /dev/null   # host only
+  echo "bench_writer exit $?"; cat gpurun_out/writer_box_host_bench.json
 fi
 
 if [[ "$ARGS" == *" trace "* ]]; then
