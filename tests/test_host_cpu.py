@@ -226,6 +226,13 @@ def test_default_writer_emits_the_bytes_of_pickle_dump(tmp_path, monkeypatch):
     rp._dump_record(big, a, False)
     pickle.dump(big, b)
     assert a.getvalue() == b.getvalue()
+    # storages beyond the cut-off take torch's own path (no template, no probe storage of that size)
+    huge = {"caption": "huge", "related_embeddings": torch.randn(1025, 1024, generator=g)}
+    known = set(rp._STORAGE_TEMPLATES)
+    a, b = io.BytesIO(), io.BytesIO()
+    rp._dump_record(huge, a, False)
+    pickle.dump(huge, b)
+    assert a.getvalue() == b.getvalue() and set(rp._STORAGE_TEMPLATES) == known
     # a template that does not reproduce torch's bytes is dropped, not used
     monkeypatch.setattr(rp, "_STORAGE_TEMPLATES", {})
     monkeypatch.setattr(rp, "_storage_template", lambda dtype, numel: (b"not", b"torch's", b"bytes"))

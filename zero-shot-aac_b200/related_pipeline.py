@@ -425,6 +425,9 @@ class _FastTensorPickler(pickle.Pickler):
 # first tensor it is used on is dropped.  ZSAAC_TEMPLATE_PICKLE=0 restores the literal
 # `pickle.dump`.
 _TEMPLATE_DTYPES = frozenset(_STORAGE_DTYPES.values())
+# beyond this the ~100 us of torch's own path no longer matter, and a template costs a probe storage
+# of the same size
+_TEMPLATE_MAX_BYTES = 4 << 20
 _STORAGE_TEMPLATES: dict = {}       # (dtype, element count) -> (head, middle, tail) | False
 
 
@@ -470,6 +473,8 @@ def _reduce_plain_tensor(t: torch.Tensor):
             and not torch.serialization._serialization_tls.skip_data):
         storage = t.untyped_storage()
         nbytes = storage.nbytes()
+        if nbytes > _TEMPLATE_MAX_BYTES:
+            return t.__reduce_ex__(pickle.DEFAULT_PROTOCOL)
         numel = nbytes // t.element_size()
         key = (t.dtype, numel)
         template = _STORAGE_TEMPLATES.get(key)
