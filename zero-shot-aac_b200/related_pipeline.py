@@ -488,6 +488,8 @@ def _reduce_plain_tensor(t: torch.Tensor):
             if first_use and payload != t._typed_storage().__reduce__()[1][0]:
                 template = False                                   # not torch's bytes: never used
         if first_use:
+            if len(_STORAGE_TEMPLATES) >= 4096:       # records of ever-changing sizes: stay bounded
+                _STORAGE_TEMPLATES.clear()
             _STORAGE_TEMPLATES[key] = template
         if template:
             return (torch._utils._rebuild_tensor_v2,
