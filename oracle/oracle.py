@@ -128,6 +128,13 @@ def sound_effect_choice(prefix: torch.Tensor, sound_effect_embeddings: torch.Ten
     return index
 
 
+# models/caption_model.py:15-21 (copies at :277-283, :414-420): the method form, called by clap_to_gpt
+def sound_effect_choice_method(prefix: torch.Tensor, sound_effect_embeddings: torch.Tensor, choice_num: int
+                               ) -> torch.Tensor:
+    index = sound_effect_choice(prefix, sound_effect_embeddings, choice_num)            # :17-19
+    return sound_effect_embeddings[index].squeeze(1)                                    # :21
+
+
 # utils.py:19-31 (Gaussian branch) — used to make BASELINE config-5 style queries
 def noise_injection(x: torch.Tensor, variance: float = 0.001, generator: Optional[torch.Generator] = None
                     ) -> torch.Tensor:

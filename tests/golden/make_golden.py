@@ -164,6 +164,27 @@ def run_sec_case(name, case):
     print(f"{name}: index[0]={idx[0].tolist()}")
 
 
+# the METHOD form of the same retrieval (models/caption_model.py:15-21): returns bank[index].squeeze(1)
+SEC_METHOD_CASES = {
+    "sound_effect_method_b4": dict(seed=2003, q=4, labels=527, k=3, lead=(4,)),
+    "sound_effect_method_b4x1": dict(seed=2004, q=4, labels=527, k=3, lead=(4, 1)),
+    "sound_effect_method_k1": dict(seed=2005, q=6, labels=527, k=1, lead=(6,)),
+}
+
+
+def run_sec_method_case(name, case):
+    sys.path.insert(0, REF)
+    from models.caption_model import ClapCaptionModel      # /root/reference/models/caption_model.py
+    prefix, bank = make_sec_inputs(case)
+    prefix_t = torch.from_numpy(prefix).reshape(*case["lead"], D)
+    out = ClapCaptionModel.sound_effect_choice(None, prefix_t, torch.from_numpy(bank), case["k"])
+    flat = out.reshape(-1, D)
+    index = (flat @ torch.from_numpy(bank).T).argmax(dim=1)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), shape=np.array(out.shape, np.int64),
+                        index=index.numpy(), rowsum=flat.double().sum(dim=1).numpy())
+    print(f"{name}: out shape {tuple(out.shape)} first rows {index[:3].tolist()}")
+
+
 RETRIEVAL_CASES = {
     "retrieval_metrics": dict(seed=3001, audios=60, clusters=6, sigma_in=0.5, noise=6.0),
     "retrieval_metrics_easy": dict(seed=3002, audios=37, clusters=37, sigma_in=0.0, noise=0.9),
@@ -281,6 +302,9 @@ if __name__ == "__main__":
     for n, c in CASES.items():
         if not only or n in only:
             run_generator_case(n, c)
+    for n, c in SEC_METHOD_CASES.items():
+        if not only or n in only:
+            run_sec_method_case(n, c)
     for n, c in SEC_CASES.items():
         if not only or n in only:
             run_sec_case(n, c)

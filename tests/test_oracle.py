@@ -155,3 +155,25 @@ def test_map2memory_matches_reference_golden(name, tmp_path):
         pickle.dump([{"caption": "listed", "text_embedding": torch.from_numpy(bank[9:10] * 3.0)}], f)
     mem = oracle.construct_support_memory([str(p)])
     np.testing.assert_allclose(mem.numpy(), g["memory"], atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(recipes.SEC_METHOD_CASES))
+def test_sound_effect_method_matches_reference_golden(name, monkeypatch):
+    """models/caption_model.py:15-21 — the caption models' method returns the chosen label
+    EMBEDDINGS, `bank[index].squeeze(1)`.  Golden from the reference's own method; checked here for
+    the oracle's restatement and for the product mirror's shape / gather logic (its ranking — one
+    CUDA launch — replaced by the oracle's)."""
+    case = recipes.SEC_METHOD_CASES[name]
+    prefix, bank = recipes.make_sec_inputs(case)
+    g = helpers.golden(name)
+    prefix_t = torch.from_numpy(prefix).reshape(*case["lead"], helpers.D)
+    bank_t = torch.from_numpy(bank)
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200 import utils
+    monkeypatch.setattr(utils, "_choice_index", lambda p, b, k: oracle.sound_effect_choice(p, b, k))
+    for out in (oracle.sound_effect_choice_method(prefix_t, bank_t, case["k"]),
+                utils.sound_effect_embeddings_choice(prefix_t, bank_t, case["k"])):
+        assert list(out.shape) == g["shape"].tolist() and out.dtype == torch.float32
+        flat = out.reshape(-1, helpers.D)
+        assert torch.equal(flat, bank_t[torch.from_numpy(g["index"])])        # the reference's rows, bit for bit
+        np.testing.assert_allclose(flat.double().sum(dim=1).numpy(), g["rowsum"], rtol=0, atol=1e-12)
