@@ -135,6 +135,32 @@ def sound_effect_choice_method(prefix: torch.Tensor, sound_effect_embeddings: to
     return sound_effect_embeddings[index].squeeze(1)                                    # :21
 
 
+# utils.py:138-208 — prompt text assembly around the label retrieval (mask_probability = 0 branch:
+# every selected label is kept) and the padding of the token lists, as dataset/dataset.py's
+# __getitem__ (:365-368) and collate (:632-647) use them
+def parse_entities(tokenizer, detected_entities: Sequence[str], mask_probability=0) -> torch.Tensor:
+    if mask_probability != 0:
+        raise NotImplementedError("the oracle restates the deterministic branch only")
+    if len(detected_entities) == 0:
+        prompt = "There are something in this audio."                                   # :162-163
+    else:
+        prompt = "There are" + ",".join(" " + e for e in detected_entities) + " in this audio."   # :165-169
+    return torch.tensor(tokenizer.encode(prompt))                                       # :171
+
+
+def padding_captions(hard_prompts: Sequence[torch.Tensor], hard_prompts_length: Sequence[int]
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    max_length = max(hard_prompts_length)                                               # :190
+    out = []
+    for h in hard_prompts:
+        pad = max_length - h.shape[0]
+        out.append(torch.cat((h, torch.zeros(pad, dtype=torch.int64) - 1)) if pad >= 0 else h[:max_length])
+    out = torch.stack(out)                                                              # :201
+    mask = out.ge(0)
+    out[~mask] = 0
+    return out, mask.float()                                                            # :202-208
+
+
 # utils.py:19-31 (Gaussian branch) — used to make BASELINE config-5 style queries
 def noise_injection(x: torch.Tensor, variance: float = 0.001, generator: Optional[torch.Generator] = None
                     ) -> torch.Tensor:

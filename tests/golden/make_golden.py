@@ -185,6 +185,62 @@ def run_sec_method_case(name, case):
     print(f"{name}: out shape {tuple(out.shape)} first rows {index[:3].tolist()}")
 
 
+# the label retrieval at its real call site: Dataset.__getitem__ (dataset/dataset.py:365-368) per
+# sample, then collate (:632-647) — what zsaac_b200.dataset.collate_with_sound_effects replaces
+COLLATE_CASES = {
+    "collate_train_b6": dict(seed=2101, q=6, labels=527, k=3, training=True),
+    "collate_eval_b3": dict(seed=2102, q=3, labels=527, k=4, training=False),
+}
+
+
+class WordTokenizer:
+    """Stand-in for the GPT-2 tokenizer (no network here): one deterministic id per word."""
+
+    def encode(self, text):
+        return [sum(ord(c) * (j + 1) for j, c in enumerate(w)) % 50257 for w in text.split()]
+
+
+def collate_labels(case):
+    rs = np.random.RandomState(case["seed"] + 7)
+    words = ["dog", "bark", "rain", "engine", "speech", "music", "door", "bird", "water", "wind"]
+    return [" ".join(words[j] for j in rs.randint(0, len(words), size=1 + i % 3)).title() for i in range(case["labels"])]
+
+
+def collate_samples(case):
+    """(prefixes [q,1,d], bank, labels, per-sample leading elements) — shared with the tests."""
+    prefix, bank = make_sec_inputs(case)
+    prefixes = torch.from_numpy(prefix).reshape(case["q"], 1, D)
+    if case["training"]:
+        lead = [(torch.arange(5) + 10 * n, torch.ones(5) * (n % 2)) for n in range(case["q"])]
+    else:
+        lead = [(f"audio_{n}.wav",) for n in range(case["q"])]
+    return prefixes, torch.from_numpy(bank), collate_labels(case), lead
+
+
+def run_collate_case(name, case):
+    sys.path.insert(0, REF)
+    import utils as ref_utils
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "dataset/dataset.py")).read())
+    ns = {"torch": torch, "padding_captions": ref_utils.padding_captions}
+    for node in tree.body:                        # dataset.py does not import under transformers 5.x
+        if isinstance(node, ast.FunctionDef) and node.name == "collate":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "dataset/dataset.py", "exec"), ns)
+    prefixes, bank, labels, lead = collate_samples(case)
+    tok = WordTokenizer()
+    batch = []
+    for n in range(case["q"]):                    # dataset/dataset.py:365-368, verbatim
+        prefix = prefixes[n]
+        sound_effects_index = ref_utils.sound_effect_choice(prefix, bank, case["k"]).squeeze(0)
+        selected_labels = [labels[i].lower() for i in list(sound_effects_index)]
+        hard_prompt = ref_utils.parse_entities(tok, selected_labels, 0)
+        batch.append((*lead[n], prefix, hard_prompt, len(hard_prompt)))
+    out = ns["collate"](batch)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), hard_prompt=out[-2].numpy(), mask=out[-1].numpy(),
+                        prefix_sum=out[-3].double().sum().item())
+    print(f"{name}: padded hard prompts {tuple(out[-2].shape)}")
+
+
 RETRIEVAL_CASES = {
     "retrieval_metrics": dict(seed=3001, audios=60, clusters=6, sigma_in=0.5, noise=6.0),
     "retrieval_metrics_easy": dict(seed=3002, audios=37, clusters=37, sigma_in=0.0, noise=0.9),
@@ -302,6 +358,9 @@ if __name__ == "__main__":
     for n, c in CASES.items():
         if not only or n in only:
             run_generator_case(n, c)
+    for n, c in COLLATE_CASES.items():
+        if not only or n in only:
+            run_collate_case(n, c)
     for n, c in SEC_METHOD_CASES.items():
         if not only or n in only:
             run_sec_method_case(n, c)

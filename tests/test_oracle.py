@@ -177,3 +177,43 @@ def test_sound_effect_method_matches_reference_golden(name, monkeypatch):
         flat = out.reshape(-1, helpers.D)
         assert torch.equal(flat, bank_t[torch.from_numpy(g["index"])])        # the reference's rows, bit for bit
         np.testing.assert_allclose(flat.double().sum(dim=1).numpy(), g["rowsum"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(recipes.COLLATE_CASES))
+def test_collate_mirror_matches_the_reference_collate_golden(name, monkeypatch):
+    """Golden: the reference's own __getitem__ lines (dataset/dataset.py:365-368: sound_effect_choice
+    + parse_entities per sample) followed by its own collate (:632-647).  Checked here: the oracle's
+    restatement of the two text helpers, and zsaac_b200.dataset.collate_with_sound_effects — ONE
+    batched retrieval in collate — with its ranking (one CUDA launch) replaced by the oracle's."""
+    case = recipes.COLLATE_CASES[name]
+    g = helpers.golden(name)
+    prefixes, bank, labels, lead = recipes.collate_samples(case)
+    tok = recipes.WordTokenizer()
+    # the reference's order of work, through the oracle's restatements
+    hard = []
+    for n in range(case["q"]):
+        idx = oracle.sound_effect_choice(prefixes[n], bank, case["k"]).squeeze(0)
+        hard.append(oracle.parse_entities(tok, [labels[i].lower() for i in list(idx)], 0))
+    hp, hm = oracle.padding_captions(hard, [len(h) for h in hard])
+    assert np.array_equal(hp.numpy(), g["hard_prompt"]) and np.array_equal(hm.numpy(), g["mask"])
+    # the product's collate on samples WITHOUT the two trailing elements
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200 import utils
+    from zsaac_b200.dataset import collate_with_sound_effects
+    from zsaac_b200.dataset import dataset as ds_mod
+    fake = lambda p, b, k: oracle.sound_effect_choice(p, b, k)     # noqa: E731  (indices on the CPU, like the mirror)
+    monkeypatch.setattr(utils, "sound_effect_choice", fake)
+    monkeypatch.setattr(ds_mod, "sound_effect_choice", fake)
+    batch = [(*lead[n], prefixes[n]) for n in range(case["q"])]
+    out = collate_with_sound_effects(batch, sound_effect_embeddings=bank, sound_effect_labels=labels,
+                                     sound_effect_num=case["k"], tokenizer=tok,
+                                     parse_entities=oracle.parse_entities, padding_captions=oracle.padding_captions)
+    assert len(out) == (5 if case["training"] else 4)
+    assert np.array_equal(out[-2].numpy(), g["hard_prompt"]) and np.array_equal(out[-1].numpy(), g["mask"])
+    assert tuple(out[-3].shape) == (case["q"], 1, helpers.D)
+    assert abs(out[-3].double().sum().item() - float(g["prefix_sum"])) < 1e-9
+    if case["training"]:
+        assert torch.equal(out[0], torch.stack([lead[n][0] for n in range(case["q"])]))
+        assert torch.equal(out[1], torch.stack([lead[n][1] for n in range(case["q"])]))
+    else:
+        assert out[0] == tuple(lead[n][0] for n in range(case["q"]))
