@@ -217,3 +217,35 @@ def test_collate_mirror_matches_the_reference_collate_golden(name, monkeypatch):
         assert torch.equal(out[1], torch.stack([lead[n][1] for n in range(case["q"])]))
     else:
         assert out[0] == tuple(lead[n][0] for n in range(case["q"]))
+
+
+@pytest.mark.parametrize("name", list(recipes.MEMORY_CASES))
+def test_construct_support_memory_host_side_matches_golden(name, tmp_path, monkeypatch):
+    """predict_prompt.construct_support_memory's HOST side (the reader loop of predict_prompt.py:30-47
+    through dataset.read_related_records, the concatenation) on the stream the reference's golden
+    was made from; the normalisation — a CUDA kernel in the product — done by torch here."""
+    import pickle
+    import zsaac_b200  # noqa: F401
+    from zsaac_b200 import predict_prompt as pp
+    _, bank = recipes.make_memory_inputs(recipes.MEMORY_CASES[name])
+    g = helpers.golden(name)
+    p = tmp_path / "mem.pkl"
+    caps = ["too short", "a caption that has exactly eight words in it", " ".join(["w"] * 25),
+            "another caption with nine words in it right here now"]
+    with open(p, "wb") as f:
+        for i, c in enumerate(caps):
+            pickle.dump({"caption": c, "text_embedding": torch.from_numpy(bank[i:i + 1] * (i + 2.0))}, f)
+        pickle.dump([{"caption": "listed", "text_embedding": torch.from_numpy(bank[9:10] * 3.0)}], f)
+
+    class Normalizer:
+        def normalize_rows(self, x):
+            return torch.nn.functional.normalize(x, dim=-1)
+
+    real_to = torch.Tensor.to
+    monkeypatch.setattr(pp, "_require_cuda", lambda: None)
+    monkeypatch.setattr(pp, "_helper", lambda device: Normalizer())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: self if (a and a[0] == "cuda") else real_to(self, *a, **k))
+    mem = pp.construct_support_memory([str(p)])
+    assert tuple(mem.shape) == tuple(g["memory"].shape)
+    assert (mem - torch.from_numpy(g["memory"])).abs().max().item() < 1e-6
