@@ -717,3 +717,58 @@ def test_bench_sharded_protocol_on_standins(world, balance):
         assert line["details"]["shard_balance"] is None
     for w in line["workloads"]:
         assert w["parity_gate"]["ok"] and w["parity_gate"]["ranks"]["identical_on_all_ranks"]
+
+
+def test_default_writer_bytes_fuzz():
+    """Random record structures (hypothesis): the template writer's stream is pickle.dump's, byte
+    for byte — tensors of every supported dtype, views with offsets and strides, storages shared
+    inside a record, long / non-ASCII strings, nested containers, big ints."""
+    import io
+    import pickle
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from zsaac_b200 import related_pipeline as rp
+
+    dtypes = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int64, torch.int32,
+              torch.int16, torch.int8, torch.uint8, torch.bool]
+
+    @st.composite
+    def tensors(draw):
+        dtype = draw(st.sampled_from(dtypes))
+        shape = draw(st.lists(st.integers(0, 6), min_size=0, max_size=3))
+        seed = draw(st.integers(0, 2 ** 16))
+        g = torch.Generator().manual_seed(seed)
+        t = (torch.randn(tuple(shape), generator=g) * 50).to(dtype)
+        op = draw(st.sampled_from(["plain", "t", "slice", "step", "row", "expand"]))
+        if op == "t" and t.dim() >= 2:
+            t = t.transpose(0, 1)
+        elif op == "slice" and t.dim() >= 1 and t.shape[0] > 1:
+            t = t[1:]
+        elif op == "step" and t.dim() >= 1 and t.shape[-1] > 1:
+            t = t[..., ::2]
+        elif op == "row" and t.dim() >= 2 and t.shape[0] > 0:
+            t = t[t.shape[0] - 1]
+        elif op == "expand" and t.dim() >= 1:
+            t = t.unsqueeze(0).expand(3, *t.shape)
+        return t
+
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(-2 ** 70, 2 ** 70), st.floats(allow_nan=False),
+                        st.text(max_size=300), st.binary(max_size=40))
+    values = st.recursive(st.one_of(scalars, tensors()),
+                          lambda inner: st.one_of(st.lists(inner, max_size=4), st.tuples(inner, inner),
+                                                  st.dictionaries(st.text(max_size=8), inner, max_size=3)),
+                          max_leaves=8)
+    records = st.dictionaries(st.text(min_size=1, max_size=12), values, min_size=0, max_size=6)
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(records, st.booleans())
+    def check(record, share):
+        if share:                                       # the same tensor object / storage twice
+            first = next((v for v in record.values() if isinstance(v, torch.Tensor)), None)
+            if first is not None:
+                record = dict(record, again=first, view=first.reshape(-1)[:1] if first.is_contiguous() else first)
+        a, b = io.BytesIO(), io.BytesIO()
+        rp._dump_record(record, a, False)
+        pickle.dump(record, b)
+        assert a.getvalue() == b.getvalue()
+
+    check()
