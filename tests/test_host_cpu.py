@@ -772,3 +772,56 @@ def test_default_writer_bytes_fuzz():
         assert a.getvalue() == b.getvalue()
 
     check()
+
+
+def test_fast_reader_fuzz():
+    """Random records through pickle.dump, read back by pickle.load and by the direct parser (with
+    its remembered stream templates warm and cold): same structure, dtypes, shapes, strides, values."""
+    import io
+    import pickle
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from zsaac_b200 import related_pipeline as rp
+
+    dtypes = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int64, torch.int32,
+              torch.int16, torch.int8, torch.uint8, torch.bool]
+
+    @st.composite
+    def tensors(draw):
+        dtype = draw(st.sampled_from(dtypes))
+        shape = draw(st.lists(st.integers(0, 5), min_size=0, max_size=3))
+        g = torch.Generator().manual_seed(draw(st.integers(0, 2 ** 16)))
+        t = (torch.randn(tuple(shape), generator=g) * 50).to(dtype)
+        op = draw(st.sampled_from(["plain", "t", "slice", "step"]))
+        if op == "t" and t.dim() >= 2:
+            t = t.transpose(0, 1)
+        elif op == "slice" and t.dim() >= 1 and t.shape[0] > 1:
+            t = t[1:]
+        elif op == "step" and t.dim() >= 1 and t.shape[-1] > 1:
+            t = t[..., ::2]
+        return t
+
+    values = st.one_of(st.none(), st.integers(-10 ** 6, 10 ** 6), st.text(max_size=20), tensors(),
+                       st.lists(tensors(), max_size=3))
+    records = st.lists(st.dictionaries(st.text(min_size=1, max_size=8), values, max_size=5), max_size=4)
+
+    def same(x, y):
+        if isinstance(y, torch.Tensor):
+            return (type(x) is torch.Tensor and x.dtype == y.dtype and x.shape == y.shape
+                    and x.stride() == y.stride() and torch.equal(x, y) and not x.requires_grad)
+        if isinstance(y, dict):
+            return isinstance(x, dict) and list(x) == list(y) and all(same(x[k], y[k]) for k in y)
+        if isinstance(y, list):
+            return isinstance(x, list) and len(x) == len(y) and all(same(a, b) for a, b in zip(x, y))
+        return type(x) is type(y) and x == y
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(records, st.booleans())
+    def check(recs, cold):
+        if cold:
+            rp._READ_TEMPLATES.clear()
+        blob = pickle.dumps(recs)
+        want = pickle.loads(blob)
+        got = rp._FastTensorUnpickler(io.BytesIO(blob)).load()
+        assert same(got, want)
+
+    check()
