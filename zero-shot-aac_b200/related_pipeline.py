@@ -443,10 +443,9 @@ def _reduce_storage_bytes(stub: _LegacyStorageBytes):
     return (torch.storage._load_from_bytes, (stub.payload,))
 
 
-def _key_field(cdata: int) -> bytes:
-    import struct
+def _key_field(cdata: int, _pack=__import__("struct").Struct("<I").pack) -> bytes:
     ident = str(cdata).encode()
-    return b"X" + struct.pack("<I", len(ident)) + ident          # BINUNICODE, as protocol 2 writes it
+    return b"X" + _pack(len(ident)) + ident                      # BINUNICODE, as protocol 2 writes it
 
 
 def _storage_template(dtype: torch.dtype, numel: int):
@@ -462,29 +461,36 @@ def _storage_template(dtype: torch.dtype, numel: int):
     return tuple(parts) if len(parts) == 3 else False
 
 
-def _reduce_plain_tensor(t: torch.Tensor):
+# (looked up once: this runs three times per record)
+_get_obj_state = torch._utils._get_obj_state
+_get_tensor_metadata = torch._C._get_tensor_metadata          # what torch._utils.get_tensor_metadata calls
+_serialization_tls = torch.serialization._serialization_tls
+_rebuild_tensor_v2 = torch._utils._rebuild_tensor_v2
+_strided = torch.strided
+
+
+def _reduce_plain_tensor(t: torch.Tensor, _string_at=__import__("ctypes").string_at,
+                         _ordered_dict=__import__("collections").OrderedDict):
     """dispatch_table entry for exactly torch.Tensor: the tuple Tensor.__reduce_ex__ returns, with
     the storage bytes filled into the template instead of produced by a torch.save call."""
-    import collections
-    import ctypes
-    if (t.device.type == "cpu" and t.layout is torch.strided and t.dtype in _TEMPLATE_DTYPES
-            and not t.requires_grad and not t.has_names() and not torch._utils._get_obj_state(t)
-            and not torch._utils.get_tensor_metadata(t)
-            and not torch.serialization._serialization_tls.skip_data):
+    if (t.device.type == "cpu" and t.layout is _strided and t.dtype in _TEMPLATE_DTYPES
+            and not t.requires_grad and not t.has_names() and not _get_obj_state(t)
+            and not _get_tensor_metadata(t) and not _serialization_tls.skip_data):
         storage = t.untyped_storage()
         nbytes = storage.nbytes()
         if nbytes > _TEMPLATE_MAX_BYTES:
             return t.__reduce_ex__(pickle.DEFAULT_PROTOCOL)
-        numel = nbytes // t.element_size()
+        size = t.element_size()
+        numel = nbytes // size
         key = (t.dtype, numel)
         template = _STORAGE_TEMPLATES.get(key)
         first_use = template is None
         if first_use:
-            template = _storage_template(t.dtype, numel) if numel * t.element_size() == nbytes else False
+            template = _storage_template(t.dtype, numel) if numel * size == nbytes else False
         if template:
             field = _key_field(storage._cdata)
             payload = b"".join((template[0], field, template[1], field, template[2],
-                                ctypes.string_at(storage.data_ptr(), nbytes) if nbytes else b""))
+                                _string_at(storage.data_ptr(), nbytes) if nbytes else b""))
             if first_use and payload != t._typed_storage().__reduce__()[1][0]:
                 template = False                                   # not torch's bytes: never used
         if first_use:
@@ -492,14 +498,13 @@ def _reduce_plain_tensor(t: torch.Tensor):
                 _STORAGE_TEMPLATES.clear()
             _STORAGE_TEMPLATES[key] = template
         if template:
-            return (torch._utils._rebuild_tensor_v2,
+            return (_rebuild_tensor_v2,
                     (_LegacyStorageBytes(payload), t.storage_offset(), tuple(t.size()), t.stride(),
-                     False, collections.OrderedDict()))
+                     False, _ordered_dict()))
     return t.__reduce_ex__(pickle.DEFAULT_PROTOCOL)
 
 
-def _template_dump(item, file) -> None:
-    import copyreg
+def _template_dump(item, file, copyreg=__import__("copyreg")) -> None:
     pickler = pickle.Pickler(file)
     table = dict(copyreg.dispatch_table)
     table[torch.Tensor] = _reduce_plain_tensor
@@ -508,9 +513,8 @@ def _template_dump(item, file) -> None:
     pickler.dump(item)
 
 
-def _template_pickle_enabled() -> bool:
-    import os
-    return os.environ.get("ZSAAC_TEMPLATE_PICKLE", "1") != "0"
+def _template_pickle_enabled(_environ=__import__("os").environ) -> bool:
+    return _environ.get("ZSAAC_TEMPLATE_PICKLE", "1") != "0"
 
 
 def _dump_record(item: dict, file, fast: bool) -> None:
